@@ -1,0 +1,134 @@
+/* veritas_b200 — C ABI of the B200-native Vlasov advance (drop-in boundary for Libbum/Veritas).
+ *
+ * The reference has no FFI: its "API" is the C++ class surface used by veritas.cpp.
+ * Each entry point below names the reference member function(s) whose body it replaces, so the
+ * reference classes become thin shells around these calls (see INTEGRATION.md and the host classes
+ * in veritas_b200/host/, which do exactly that).
+ *
+ * Conventions: every call returns 0 on success or a negative code; vrt_last_error() gives the text.
+ * Nothing throws, nothing calls exit().  One host thread per context; all device work of a context
+ * is issued on one CUDA stream.  Device memory is owned by the context, host buffers by the caller.
+ * All arithmetic is fp64.  There is no CPU fallback: without a CUDA device vrt_create() fails.
+ *
+ * Patch arrays exchanged with the host use the reference's padded layout (2 ghost cells per side,
+ * p fastest): index (n_p+4)*(i+2)+2+j for cell (i,j)  (Rectangle.hpp:105-108), one plane per state.
+ */
+#ifndef VERITAS_B200_H
+#define VERITAS_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vrt_ctx vrt_ctx;
+
+enum { VRT_OK = 0, VRT_ERR_ARG = -1, VRT_ERR_CUDA = -2, VRT_ERR_STATE = -3, VRT_ERR_NCCL = -4, VRT_ERR_NOMEM = -5 };
+
+/* field selectors for vrt_field_upload/download: the six transverse arrays of EMFieldSolver
+ * (EMSolver.hpp:18), 8 time slots each (EMSolver.hpp:51-53) */
+enum { VRT_BY = 0, VRT_BZ = 1, VRT_EY = 2, VRT_EZ = 3, VRT_AY = 4, VRT_AZ = 5 };
+/* 1-D array selectors for vrt_get_1d/vrt_set_1d */
+enum { VRT_PHI = 0, VRT_CHARGE = 1, VRT_J = 2, VRT_A_SQUARED = 3, VRT_NEUTRALIZATION = 4, VRT_EFIELD = 5,
+       VRT_CHARGES0 = 16 /* + species index: per-species charge (EMSolver.hpp:19 `charges`) */ };
+/* scalar selectors */
+enum { VRT_EX0 = 0, VRT_TIME = 1 };
+/* Vlasov kernel selection */
+enum { VRT_PATH_AUTO = 0, VRT_PATH_SPLIT = 1 /* sub-step kernels with ghost syncs, any hierarchy */,
+       VRT_PATH_FUSED = 2 /* one streaming pass per stage; single-level full-domain patches / x-slabs */ };
+
+/* Rectangle ctor arguments (Rectangle.hpp:23): depth 0 = finest level. */
+typedef struct {
+    int depth, x_pos, p_pos, n_x, n_p;
+    int up, down, left, right;
+} vrt_patch_desc;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+/* Library-wide error text for failures that have no context yet (vrt_create). */
+const char* vrt_global_error(void);
+const char* vrt_last_error(const vrt_ctx* ctx);
+const char* vrt_version(void);
+/* SolverManager::SolverManager (SolverManager.cpp:8-26): one context = meshes + field solver on one GPU. */
+int vrt_create(vrt_ctx** out, int device, int n_species);
+int vrt_destroy(vrt_ctx* ctx);
+int vrt_sync(vrt_ctx* ctx);
+/* cudaStream_t of the context, as an opaque pointer (for callers that time with CUDA events). */
+void* vrt_stream(vrt_ctx* ctx);
+
+/* ---- configuration (Settings.cpp:5-58, EMSolver.cpp:6-27) ----------------------------------- */
+int vrt_set_grid(vrt_ctx* ctx, int x_size_finest, double dx_finest, int n_prepad, int n_postpad,
+                 int refinement_ratio, int max_depth);
+int vrt_set_species(vrt_ctx* ctx, int s, double mass, double charge, double pmin, double dp_finest);
+/* Mesh::promoteHierarchyToMesh (Mesh.cpp:794-875): (re)create the patches of species s.  Connectivity
+ * (Rectangle::CalculateConnectivitySame / FromFiner, Rectangle.cpp:671-864) is derived from the descriptors.
+ * Patch data are zero after this call. */
+int vrt_set_hierarchy(vrt_ctx* ctx, int s, int n_patches, const vrt_patch_desc* patches);
+int vrt_set_path(vrt_ctx* ctx, int path);
+int vrt_get_path(vrt_ctx* ctx, int s);
+
+/* ---- data movement (init, regrid, output) --------------------------------------------------- */
+/* state: 0 = f^n, 1 = current stage value, 2 = low-order predictor (Rectangle.hpp:96-98). */
+int vrt_patch_upload_f(vrt_ctx* ctx, int s, int patch, int state, const double* host_padded);
+int vrt_patch_download_f(vrt_ctx* ctx, int s, int patch, int state, double* host_padded);
+/* Rectangle::FCTTimeStep(…,3) applied to every patch (Mesh.cpp:869-874): f0 := f1 on the padded array. */
+int vrt_commit_state(vrt_ctx* ctx, int s);
+int vrt_field_upload(vrt_ctx* ctx, int which, int slot, const double* host);   /* M = x_size+pads doubles */
+int vrt_field_download(vrt_ctx* ctx, int which, int slot, double* host);
+int vrt_set_1d(vrt_ctx* ctx, int which, const double* host);
+int vrt_get_1d(vrt_ctx* ctx, int which, double* host);   /* VRT_A_SQUARED: x_size+1, others x_size */
+int vrt_set_scalar(vrt_ctx* ctx, int which, double v);
+int vrt_get_scalar(vrt_ctx* ctx, int which, double* v);
+
+/* ---- the hot path --------------------------------------------------------------------------- */
+/* EMFieldSolver::AssembleRhoAndJ (EMSolver.cpp:104-122) -> Mesh::InterpolateRhoAndJToFinestMesh (Mesh.cpp:52-56)
+ * -> Level::CollectRhoAndJ (Level.cpp:42-62) -> Rectangle::CalculateRhoAndJ (Rectangle.cpp:157-282). */
+int vrt_moments(vrt_ctx* ctx);
+/* EMFieldSolver::EnforceChargeNeutralization (EMSolver.cpp:621-629). */
+int vrt_enforce_neutralization(vrt_ctx* ctx);
+/* EMFieldSolver::UpdatePotential (EMSolver.cpp:156-192): periodic 4th-order Poisson + Ex0 update.  The
+ * reference's dense LU (EMSolver.cpp:28-86) is replaced by an O(N) direct solve of the same linear system. */
+int vrt_poisson(vrt_ctx* ctx);
+/* Mesh::Advance(dt, step) (Mesh.cpp:64-89) for species s. */
+int vrt_vlasov_stage(vrt_ctx* ctx, int s, double dt, int step);
+/* Level::FCTTimeStep(dt, step, subStep) (Level.cpp:12-17 -> Rectangle.cpp:1255-1623); level = depth. */
+int vrt_vlasov_substep(vrt_ctx* ctx, int s, int depth, double dt, int step, int substep);
+/* Mesh::PushData(val) (Mesh.cpp:91-106) and Mesh::PushBoundaryC() (Mesh.cpp:904-917). */
+int vrt_push_data(vrt_ctx* ctx, int s, int val);
+int vrt_push_boundary_c(vrt_ctx* ctx, int s);
+/* EMFieldSolver::RGKStep(step, dt) (EMSolver.cpp:194-202) = RGKCalculateRHS + RGKUpdateIntermediateSolution +
+ * InterpolateToFaces; by0/bz0 are the host-evaluated Settings::GetBY/GetBZ(0, time) (EMSolver.cpp:501-502). */
+int vrt_field_stage(vrt_ctx* ctx, int step, double dt, double by0, double bz0);
+/* EMFieldSolver::EstimateCFLBound (EMSolver.cpp:631-664). */
+int vrt_cfl_bound(vrt_ctx* ctx, double* out);
+/* Settings::UpdateTime(step, dt) (Settings.cpp:166-179) on the context's clock; host-side helper. */
+double vrt_update_time(double time, int step, double dt);
+/* SolverManager::Advance(dt) (SolverManager.cpp:28-39): the six stages, captured once as a CUDA graph and
+ * replayed.  laser[2*i], laser[2*i+1] = GetBY, GetBZ(0, time after UpdateTime(i)).  Advances VRT_TIME. */
+int vrt_step(vrt_ctx* ctx, double dt, const double laser[12]);
+/* SolverManager::AdvanceFields(dt) (SolverManager.cpp:41-46). */
+int vrt_step_fields(vrt_ctx* ctx, double dt, const double laser[12]);
+/* number of kernels the last vrt_step / vrt_step_fields launched (for bench.py's gpu_launches) */
+long vrt_last_step_launches(const vrt_ctx* ctx);
+
+/* ---- multi-GPU x-slabs (no counterpart in the reference) ------------------- */
+/* This context owns finest columns [x_begin, x_end) of every full-domain single-level patch. */
+int vrt_set_slab(vrt_ctx* ctx, int rank, int n_ranks, int x_begin, int x_end);
+int vrt_nccl_unique_id(void* out128);
+int vrt_comm_init(vrt_ctx* ctx, const void* unique_id128, int rank, int n_ranks);
+
+/* ---- laser-plasma case helpers (veritas.cpp:36-115 restated in host/laser_plasma_case.hpp) --- */
+typedef struct {
+    double lambda, a0, density, temp_frac, pmax_e, pmax_i, box_lambdas, ion_mass_ratio;
+} vrt_case_params;
+typedef struct {
+    double dp[2], pmin[2], dx, sizeWeight, temp0[2], temp1[2], tempEM[2];
+    int quadratureDepth;
+} vrt_case_derived;
+int vrt_case_derive(const vrt_case_params* p, double m0, double q0, unsigned x_size, const unsigned* p_size,
+                    double refinementCriteria, vrt_case_derived* out);
+double vrt_case_laser_by(double lambda, double amp, double x, double t);
+double vrt_case_laser_bz(double lambda, double amp, double x, double t);
+double vrt_case_maxwellian_slab(double x, double p, double xl, double xr, double n0, double T);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VERITAS_B200_H */

@@ -1,0 +1,204 @@
+// TEST INFRASTRUCTURE — oracle harness.  Not part of the product; nothing under veritas_b200/
+// links or calls it.  It drives the UNMODIFIED reference classes (compiled from where they lie
+// under /root/reference by oracle/Makefile into oracle/_ref/) and dumps full-precision state so
+// that the C restatement (oracle/veritas_oracle.c) and the CUDA path can be checked against the
+// reference's own CPU solver.
+//
+// The reference is configured by editing its case file (docs/index.rst:114-160): this file plays
+// the role of /root/reference/veritas.cpp — it supplies main() and the user-defined members of
+// Settings (settingsOverride, RefinementOverride, GetBY, GetBZ, InitialDistribution), taking the
+// laser-plasma case from veritas_b200/host/laser_plasma_case.hpp.  Private members of
+// SolverManager / EMFieldSolver / Rectangle are read with g++ -fno-access-control.
+//
+// usage: ref_harness out.bin nx np Lfinest density steps [key=value ...]
+//   keys: dump_every=1 stage_dumps=0 regrid_every=0 threads=N refine_mode=0 tail_p0=2 pre_steps=-1
+//         time_only=0 internals=0 a0=1
+#include "veritas.hpp"
+#include "Settings.hpp"
+#include "SolverManager.hpp"
+#include "EMSolver.hpp"
+#include "Mesh.hpp"
+#include "Level.hpp"
+#include "Rectangle.hpp"
+#include "../veritas_b200/host/laser_plasma_case.hpp"
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <string>
+
+bool LOUD = false, NOISY = false;
+static vrt_case::LaserPlasma g_case;
+
+void Settings::settingsOverride() {
+    unsigned ps[2] = {p_size[0], p_size[1]};
+    vrt_case::Derived d = vrt_case::derive(g_case, m[0], q[0], x_size, ps, refinementCriteria);
+    dp[0] = d.dp[0]; dp[1] = d.dp[1];
+    pmin[0] = d.pmin[0]; pmin[1] = d.pmin[1];
+    dx = d.dx;
+    sizeWeight = d.sizeWeight;
+    quadratureDepth = d.quadratureDepth;
+    temp[0].resize(2, 0.0); temp[0][0] = d.temp0[0]; temp[0][1] = d.temp1[0];
+    temp[1].resize(2, 0.0); temp[1][0] = d.temp0[1]; temp[1][1] = d.temp1[1];
+    tempEM.resize(2, 0.0); tempEM[0] = d.tempEM[0]; tempEM[1] = d.tempEM[1];
+}
+bool Settings::RefinementOverride(double x, double p, int depth, int particleType) {
+    return vrt_case::refine_override(g_case, x, p, temp[particleType][1], m[0]);
+}
+double Settings::GetBY(double x, double t) { return vrt_case::laser_by(tempEM[0], tempEM[1], x, t); }
+double Settings::GetBZ(double x, double t) { return vrt_case::laser_bz(tempEM[0], tempEM[1], x, t); }
+double Settings::InitialDistribution(double x, double p, int particleType) {
+    return vrt_case::maxwellian_slab(x, p, plasma_xl_bound, plasma_xr_bound, temp[particleType][0], temp[particleType][1]);
+}
+
+// ---- tiny binary container: records of  name | ndim | dims | float64 data -------------------
+static FILE* g_out = nullptr;
+static void put(const std::string& name, const double* data, std::initializer_list<long> dims) {
+    unsigned nl = name.size(), nd = dims.size();
+    fwrite(&nl, 4, 1, g_out); fwrite(name.data(), 1, nl, g_out); fwrite(&nd, 4, 1, g_out);
+    long n = 1;
+    for (long d : dims) { fwrite(&d, 8, 1, g_out); n *= d; }
+    fwrite(data, 8, n, g_out);
+}
+static void put1(const std::string& name, double v) { put(name, &v, {1}); }
+
+static void dump_state(SolverManager& SM, Settings& st, const std::string& tag, bool internals) {
+    EMFieldSolver& em = *SM.EMSolver;
+    long M = em.x_size + em.n_prepad + em.n_postpad, N = em.x_size;
+    put1(tag + "/time", st.time);
+    put(tag + "/By", em.By.data(), {8, M}); put(tag + "/Bz", em.Bz.data(), {8, M});
+    put(tag + "/Ey", em.Ey.data(), {8, M}); put(tag + "/Ez", em.Ez.data(), {8, M});
+    put(tag + "/Ay", em.Ay.data(), {8, M}); put(tag + "/Az", em.Az.data(), {8, M});
+    put(tag + "/a_squared", em.a_squared.data(), {N + 1});
+    put(tag + "/PHI", em.PHI, {N});
+    put1(tag + "/Ex0", em.Ex0);
+    put(tag + "/charge", em.charge.data(), {N});
+    put(tag + "/J", em.J.data(), {N});
+    put(tag + "/neutralizationCharge", em.neutralizationCharge.data(), {N});
+    for (size_t s = 0; s < SM.meshes.size(); s++) {
+        put(tag + "/charges" + std::to_string(s), em.charges[s].data(), {N});
+        Mesh& mesh = *SM.meshes[s];
+        for (size_t l = 0; l < mesh.levels.size(); l++) {
+            auto& rects = mesh.levels[l]->rectangles;
+            for (size_t r = 0; r < rects.size(); r++) {
+                Rectangle& R = *rects[r];
+                std::string p = tag + "/s" + std::to_string(s) + "/l" + std::to_string(l) + "/r" + std::to_string(r);
+                double desc[10] = {(double)R.n_x, (double)R.n_p, (double)R.x_pos, (double)R.p_pos, (double)R.depth,
+                                   (double)R.up, (double)R.down, (double)R.left, (double)R.right, R.relativeToBottom};
+                put(p + "/desc", desc, {10});
+                put(p + "/f", R.f.data(), {R.n_x + 4, R.n_p + 4, 3});
+                if (internals) {
+                    put(p + "/FxH", R.FxH.data(), {R.n_x + 4, R.n_p + 4, 6});
+                    put(p + "/FpH", R.FpH.data(), {R.n_x + 4, R.n_p + 4, 6});
+                    put(p + "/FxL", R.FxL.data(), {R.n_x + 4, R.n_p + 4, 6});
+                    put(p + "/FpL", R.FpL.data(), {R.n_x + 4, R.n_p + 4, 6});
+                    put(p + "/FxDS", R.FxDS.data(), {R.n_x + 4, R.n_p + 4});
+                    put(p + "/FpDS", R.FpDS.data(), {R.n_x + 4, R.n_p + 4});
+                    put(p + "/Rp", R.Rp.data(), {R.n_x + 4, R.n_p + 4});
+                    put(p + "/Rm", R.Rm.data(), {R.n_x + 4, R.n_p + 4});
+                    put(p + "/Cx", R.Cx.data(), {R.n_x + 4, R.n_p + 4});
+                    put(p + "/Cp", R.Cp.data(), {R.n_x + 4, R.n_p + 4});
+                    put(p + "/ex", R.ex.data(), {R.n_x + 4, R.n_p + 4});
+                    put(p + "/ep", R.ep.data(), {R.n_x + 4, R.n_p + 4});
+                }
+            }
+        }
+    }
+}
+
+int main(int argc, char** argv) {
+    if (argc < 7) { fprintf(stderr, "usage: %s out.bin nx np Lfinest density steps [key=value...]\n", argv[0]); return 2; }
+    const char* out = argv[1];
+    unsigned nx = atoi(argv[2]), np = atoi(argv[3]), Lfinest = atoi(argv[4]);
+    g_case.density = atof(argv[5]);
+    int steps = atoi(argv[6]);
+    std::map<std::string, double> kv = {{"dump_every", 1}, {"stage_dumps", 0}, {"regrid_every", 0}, {"threads", 0},
+                                        {"refine_mode", 0}, {"tail_p0", 2}, {"pre_steps", -1}, {"time_only", 0},
+                                        {"internals", 0}, {"a0", 1}, {"np_ion", 0}};
+    for (int i = 7; i < argc; i++) {
+        std::string a = argv[i]; size_t e = a.find('=');
+        if (e == std::string::npos || !kv.count(a.substr(0, e))) { fprintf(stderr, "bad arg %s\n", argv[i]); return 2; }
+        kv[a.substr(0, e)] = atof(a.c_str() + e + 1);
+    }
+    g_case.refine_mode = (int)kv["refine_mode"]; g_case.tail_p0 = kv["tail_p0"]; g_case.a0 = kv["a0"];
+    if (kv["threads"] > 0) omp_set_num_threads((int)kv["threads"]);
+    bool time_only = kv["time_only"] != 0, internals = kv["internals"] != 0;
+
+    Input grid; Particles particles; Output output;
+    grid.minEfficiency = 0.75; grid.dx = 0.5; grid.k = 0.01;
+    grid.refinementCriteria = 1e-8; grid.cfl = 0.5; grid.sizeWeight = 0.0;
+    grid.preLength = 0; grid.postLength = 0;
+    grid.nx = nx; grid.r = 2; grid.Lfinest = Lfinest;
+    grid.tempEM = {0.0};
+    particles.mass = {9.10938291e-31, 9.10938291e-31 * 1836};
+    particles.charge = {-1.60217657e-19, 1.60217657e-19};
+    particles.misc = {{0.0, 0.01}, {0.0, 0.01}};
+    unsigned np_ion = kv["np_ion"] > 0 ? (unsigned)kv["np_ion"] : np;
+    particles.np = {np, np_ion};
+    particles.dp = {0.1, 0.1};
+    particles.pmin = {0.1, 0.1};
+
+    Settings settings(grid, particles, output);
+    SolverManager SM(settings);
+
+    if (!time_only) {
+        g_out = fopen(out, "wb");
+        if (!g_out) { perror(out); return 1; }
+    }
+    double T = settings.tempEM[0] / cs;
+    double dt = T / 400, t = dt;
+    int pre_steps = (int)kv["pre_steps"];
+    int n_pre = 0;
+    // fields-only phase, exactly as the shipped main(): while t <= 3T (veritas.cpp:135-144)
+    while (pre_steps < 0 ? !(t > 3 * T) : n_pre < pre_steps) {
+        SM.AdvanceFields(dt);
+        t += dt; n_pre++;
+    }
+    if (!time_only) {
+        double meta[8] = {(double)nx, (double)np, (double)Lfinest, g_case.density, (double)steps, (double)n_pre, dt, t};
+        put("meta", meta, {8});
+        put1("dx", settings.GetDx(0));
+        for (int s = 0; s < 2; s++) {
+            double sp[4] = {settings.m[s], settings.q[s], settings.pmin[s], settings.GetDp(0, s)};
+            put("species" + std::to_string(s), sp, {4});
+        }
+        double em[2] = {settings.tempEM[0], settings.tempEM[1]};
+        put("tempEM", em, {2});
+        dump_state(SM, settings, "step0", internals);
+    }
+    int counter = 0, regrid_every = (int)kv["regrid_every"], dump_every = (int)kv["dump_every"];
+    bool stage_dumps = kv["stage_dumps"] != 0;
+    double advance_seconds = 0.0;
+    long cells = 0;
+    for (auto& mesh : SM.meshes) for (auto& lvl : mesh->levels) for (auto& r : lvl->rectangles) cells += (long)r->n_x * r->n_p;
+    for (int n = 1; n <= steps; n++) {
+        double dt_adaptive = std::min(SM.CalculateDt(settings.cfl), dt);
+        auto t0 = std::chrono::steady_clock::now();
+        if (stage_dumps && !time_only) {
+            // SolverManager::Advance unrolled (SolverManager.cpp:28-39) with a dump after every stage
+            for (int i = 0; i < 6; i++) {
+                SM.EMSolver->AssembleRhoAndJ();
+                SM.EMSolver->UpdatePotential();
+                for (unsigned j = 0; j < settings.q.size(); j++) SM.meshes[j]->Advance(dt_adaptive, i);
+                settings.UpdateTime(i, dt_adaptive);
+                SM.EMSolver->RGKStep(i, dt_adaptive);
+                dump_state(SM, settings, "step" + std::to_string(n) + "_stage" + std::to_string(i), internals);
+            }
+        } else {
+            SM.Advance(dt_adaptive);
+        }
+        advance_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (regrid_every > 0) {
+            if (counter >= regrid_every - 1) { SM.reGrid(t); counter = 0; } else counter++;
+        }
+        t += dt_adaptive;
+        if (!time_only && (n % dump_every == 0 || n == steps)) {
+            put1("step" + std::to_string(n) + "/dt", dt_adaptive);
+            dump_state(SM, settings, "step" + std::to_string(n), internals);
+        }
+    }
+    if (g_out) fclose(g_out);
+    // machine-readable timing line (CPU baseline): cells, steps, seconds in Advance, threads
+    printf("ORACLE_TIMING cells=%ld steps=%d advance_s=%.6f threads=%d cell_updates_per_s_per_stage=%.6e\n", cells, steps,
+           advance_seconds, omp_get_max_threads(), steps > 0 ? 6.0 * (double)cells * steps / advance_seconds : 0.0);
+    return 0;
+}
