@@ -108,6 +108,13 @@ int vrt_step_fields(vrt_ctx* ctx, double dt, const double laser[12]);
 /* number of kernels the last vrt_step / vrt_step_fields launched (for bench.py's gpu_launches) */
 long vrt_last_step_launches(const vrt_ctx* ctx);
 
+/* option 0: replay vrt_step through a captured CUDA graph (default 1) or launch kernel by kernel (0) */
+int vrt_set_option(vrt_ctx* ctx, int option, int value);
+/* Rectangle::InitializeDistribution (Rectangle.cpp:616-665) for the shipped Maxwellian slab
+ * (Settings::InitialDistribution, veritas.cpp:107-115), evaluated on the device: sub-cell midpoint quadrature
+ * with r^(depth+quadrature_depth) points per direction; writes states 0 and 1.  SURVEY.md §8(f) item 2. */
+int vrt_init_maxwellian_slab(vrt_ctx* ctx, int s, double xl, double xr, double n0, double T, int quadrature_depth);
+
 /* ---- multi-GPU x-slabs (no counterpart in the reference) ------------------- */
 /* This context owns finest columns [x_begin, x_end) of every full-domain single-level patch. */
 int vrt_set_slab(vrt_ctx* ctx, int rank, int n_ranks, int x_begin, int x_end);

@@ -204,11 +204,15 @@ class SingleLevelOracle:
         F.Ex0 = float(dump[f"{tag}/Ex0"][0])
         self.time = float(dump[f"{tag}/time"][0])
         for s, P in enumerate(self.patches):
-            f = dump[f"{tag}/s{s}/l0/r0/f"]
-            P.f0[:] = f[:, :, 0]; P.f1[:] = f[:, :, 1]; P.f2[:] = f[:, :, 2]
+            base = f"{tag}/s{s}/l0/r0/"
+            if base + "f" in dump:
+                f = dump[base + "f"]
+                P.f0[:] = f[:, :, 0]; P.f1[:] = f[:, :, 1]; P.f2[:] = f[:, :, 2]
+            else:   # reduced golden fixture: states 0 and 1 only
+                P.f0[:] = dump[base + "f0"]; P.f1[:] = dump[base + "f1"]
             for k in ("FxH", "FpH"):
-                if f"{tag}/s{s}/l0/r0/{k}" in dump:
-                    P.a[k][:] = np.moveaxis(dump[f"{tag}/s{s}/l0/r0/{k}"], 2, 0)
-            if f"{tag}/s{s}/l0/r0/FxL" in dump:
-                P.FxL[:] = dump[f"{tag}/s{s}/l0/r0/FxL"][:, :, 0]
-                P.FpL[:] = dump[f"{tag}/s{s}/l0/r0/FpL"][:, :, 0]
+                if base + k in dump:
+                    P.a[k][:] = np.moveaxis(dump[base + k], 2, 0)
+            if base + "FxL" in dump:
+                P.FxL[:] = dump[base + "FxL"][:, :, 0]
+                P.FpL[:] = dump[base + "FpL"][:, :, 0]

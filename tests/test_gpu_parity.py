@@ -1,0 +1,194 @@
+"""GPU parity tests: the CUDA paths, called through the C ABI, against the oracle and the reference's golden states.
+Tolerances: f and transverse fields <= 1e-12 relative L2 per step (north_star); E_x/PHI are ill-conditioned
+ and are reported against a looser bound."""
+import numpy as np
+import pytest
+
+from common import load_golden, rel_l2, species_from, meta
+import veritas_b200 as vb
+from veritas_b200 import solver as S
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def make_ctx(d, path):
+    mt = meta(d)
+    sp = species_from(d)
+    ctx = vb.Context(2)
+    ctx.set_grid(mt["nx"], mt["dx"], 2, 2, 2, 0)
+    for s in range(2):
+        ctx.set_species(s, sp[s]["m"], sp[s]["q"], sp[s]["pmin"], sp[s]["dp"])
+    ctx.set_path(path)
+    for s in range(2):
+        ctx.set_hierarchy(s, [dict(depth=0, x_pos=0, p_pos=0, n_x=mt["nx"], n_p=mt["np"][s], up=1, down=1, left=1, right=1)])
+    return ctx, mt
+
+
+def laser_fn(mt):
+    L = vb.load()
+    return lambda t: (L.vrt_case_laser_by(mt["lam"], mt["amp"], 0.0, t), L.vrt_case_laser_bz(mt["lam"], mt["amp"], 0.0, t))
+
+
+@pytest.mark.parametrize("path", [S.PATH_SPLIT, S.PATH_FUSED])
+def test_stage_parity_with_injected_phi(path):
+    """Every RK stage of two steps against the reference's stage dumps, PHI injected so that the Vlasov kernels are
+    isolated from Poisson round-off."""
+    d = load_golden("single_64x32_stages")
+    ctx, mt = make_ctx(d, path)
+    assert ctx.get_path(0) == path
+    ctx.load_reference_state(d, "step0")
+    laser = laser_fn(mt)
+    L = vb.load()
+    t = float(d["step0/time"][0])
+    worst = {}
+    for n in range(1, mt["steps"] + 1):
+        dt = float(d[f"step{n}/dt"][0])
+        for i in range(6):
+            tag = f"step{n}_stage{i}"
+            ctx.moments()
+            ctx.set_1d(S.PHI, d[tag + "/PHI"])
+            ctx.set_scalar(S.EX0, float(d[tag + "/Ex0"][0]))
+            for s in range(2):
+                ctx.vlasov_stage(s, dt, i)
+            t = L.vrt_update_time(t, i, dt)
+            by0, bz0 = laser(t)
+            ctx.field_stage(i, dt, by0, bz0)
+            for s in range(2):
+                e = rel_l2(ctx.download_f(s, 0, 1), d[tag + f"/s{s}/l0/r0/f1"])
+                worst[f"f{s}"] = max(worst.get(f"f{s}", 0), e)
+                assert e < TOL, (tag, s, e)
+            for w, k in enumerate(S.FIELD_NAMES):
+                e = rel_l2(ctx.download_field(w, 1), d[tag + "/" + k][1])
+                worst[k] = max(worst.get(k, 0), e)
+                assert e < TOL, (tag, k, e)
+            for which, k in ((S.J, "J"), (S.CHARGE, "charge"), (S.A_SQUARED, "a_squared")):
+                e = rel_l2(ctx.get_1d(which), d[tag + "/" + k])
+                worst[k] = max(worst.get(k, 0), e)
+                assert e < 1e-11, (tag, k, e)
+    print("worst relative L2:", {k: "%.2e" % v for k, v in worst.items()})
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["single_128x64_steps", "single_96x48x24_steps"])
+@pytest.mark.parametrize("path", [S.PATH_SPLIT, S.PATH_FUSED])
+def test_per_step_parity_from_reference_state(name, path):
+    """Protocol P1: one full step (own moments, own Poisson, graph replay) from each reference state."""
+    d = load_golden(name)
+    ctx, mt = make_ctx(d, path)
+    laser = laser_fn(mt)
+    L = vb.load()
+    worst = {}
+    for n in range(1, mt["steps"] + 1):
+        ctx.load_reference_state(d, f"step{n - 1}")
+        for s in range(2):
+            ctx.commit_state(s)
+        dt = float(d[f"step{n}/dt"][0])
+        t = float(d[f"step{n - 1}/time"][0])
+        lasers = []
+        for i in range(6):
+            t = L.vrt_update_time(t, i, dt)
+            lasers += list(laser(t))
+        ctx.step(dt, lasers)
+        for s in range(2):
+            f1 = ctx.download_f(s, 0, 1)
+            e = rel_l2(f1, d[f"step{n}/s{s}/l0/r0/f1"])
+            worst[f"f{s}"] = max(worst.get(f"f{s}", 0), e)
+            assert e < TOL, (n, s, e)
+            assert np.array_equal(ctx.download_f(s, 0, 0), f1)
+        for w, k in enumerate(S.FIELD_NAMES):
+            e = rel_l2(ctx.download_field(w, 0), d[f"step{n}/{k}"][0])
+            worst[k] = max(worst.get(k, 0), e)
+            assert e < TOL, (n, k, e)
+        ex_ref = None
+        e = rel_l2(ctx.get_1d(S.PHI), d[f"step{n}/PHI"])
+        worst["PHI"] = max(worst.get("PHI", 0), e)
+        assert e < 1e-6
+        assert abs(ctx.get_scalar(S.TIME) - d[f"step{n}/time"][0]) < 1e-30
+    print(name, "worst relative L2:", {k: "%.2e" % v for k, v in worst.items()})
+    ctx.close()
+
+
+def test_fused_equals_split_free_running():
+    """Both CUDA paths, 5 free-running steps from the same state."""
+    d = load_golden("single_128x64_steps")
+    res = {}
+    for path in (S.PATH_SPLIT, S.PATH_FUSED):
+        ctx, mt = make_ctx(d, path)
+        ctx.load_reference_state(d, "step0")
+        for s in range(2):
+            ctx.commit_state(s)
+        laser = laser_fn(mt)
+        L = vb.load()
+        t = float(d["step0/time"][0])
+        for n in range(1, 6):
+            dt = float(d[f"step{n}/dt"][0])
+            lasers = []
+            for i in range(6):
+                t = L.vrt_update_time(t, i, dt)
+                lasers += list(laser(t))
+            ctx.step(dt, lasers)
+        res[path] = [ctx.download_f(s, 0, 1) for s in range(2)] + [ctx.download_field(S.EY, 0), ctx.get_1d(S.CHARGE)]
+        ctx.close()
+    for a, b in zip(res[S.PATH_SPLIT], res[S.PATH_FUSED]):
+        assert rel_l2(a, b) < 1e-12
+
+
+def test_poisson_against_dense_lu_oracle():
+    """UpdatePotential: O(N) device solve vs the oracle's dense partial-pivot LU of the reference matrix."""
+    from oracle.port import Fields, lib as olib
+    import ctypes as C
+    rng = np.random.default_rng(7)
+    for N in (64, 256, 1024):
+        dx = 1e-5 / N
+        ctx = vb.Context(1)
+        ctx.set_grid(N, dx, 2, 2, 2, 0)
+        ctx.set_species(0, S.M_E, -S.Q_E, -1.0e-21, 1e-23)
+        rho = rng.standard_normal(N) * 1e3
+        rho -= rho.mean()
+        neutral = rng.standard_normal(N) * 1e-3
+        ctx.set_1d(S.CHARGE, rho); ctx.set_1d(S.NEUTRALIZATION, neutral)
+        ctx.set_scalar(S.EX0, 0.25)
+        ctx.call("vrt_set_hierarchy", 0, 1, (vb.PatchDesc * 1)(vb.PatchDesc(depth=0, x_pos=0, p_pos=0, n_x=N, n_p=8, up=1, down=1, left=1, right=1)))
+        ctx.poisson()
+        phi = ctx.get_1d(S.PHI); E = ctx.get_1d(S.EFIELD); ex0 = ctx.get_scalar(S.EX0)
+        F = Fields(N, dx)
+        F.charge[:] = rho; F.neutral[:] = neutral; F.Ex0 = 0.25
+        Lo = olib()
+        P = Lo.vo_poisson_create(N)
+        Lo.vo_update_potential(P, C.byref(F.c))
+        Lo.vo_poisson_destroy(P)
+        Eo = F.efield()
+        assert rel_l2(E, Eo) < 1e-9, (N, rel_l2(E, Eo))
+        assert abs(ex0 - F.Ex0) <= 1e-9 * max(abs(F.Ex0), np.abs(Eo).max())
+        assert rel_l2(phi[1:], F.PHI[1:]) < 1e-8
+        ctx.close()
+
+
+def test_cfl_bound_matches_oracle():
+    from oracle.port import SingleLevelOracle
+    d = load_golden("single_128x64_steps")
+    ctx, mt = make_ctx(d, S.PATH_FUSED)
+    ctx.load_reference_state(d, "step3")
+    sp = species_from(d)
+    for s in range(2):
+        sp[s]["n_p"] = mt["np"][s]
+    O = SingleLevelOracle(mt["nx"], mt["np"][0], mt["dx"], sp, poisson=False)
+    O.load_reference_state(d, "step3")
+    assert ctx.cfl_bound() == pytest.approx(O.cfl_bound(), rel=1e-14)
+    ctx.close()
+
+
+def test_particle_number_conserved_at_scale():
+    """Size-independent property at a size the oracle does not reach in seconds: particle number per species is
+    conserved to round-off (flux form, closed walls) over several steps of the fused path."""
+    run = vb.LaserPlasmaRun(1024, 512, density=0.1)
+    run.init_device()
+    n0 = [run.ctx.download_f(s, 0, 1)[2:-2, 2:-2].sum() for s in range(2)]
+    run.time = 3 * run.T
+    for _ in range(5):
+        run.advance(run.calculate_dt())
+    for s in range(2):
+        n1 = run.ctx.download_f(s, 0, 1)[2:-2, 2:-2].sum()
+        assert abs(n1 - n0[s]) <= 1e-12 * abs(n0[s]), (s, n0[s], n1)
+    run.ctx.close()

@@ -1,0 +1,585 @@
+// C ABI of veritas_b200 (include/veritas_b200.h): context, device storage, orchestration of the stage loop.
+#include "vrt_internal.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <dlfcn.h>
+
+int vrt_fields_refresh_efield(vrt_ctx* c);
+int vrt_init_kernels_maxwellian(vrt_ctx* c, int s, double xl, double xr, double n0, double T, int quadrature_depth);
+int vrt_comm_halo_exchange(vrt_ctx* c, int s);
+int vrt_comm_gather_moments(vrt_ctx* c);
+void vrt_comm_destroy(vrt_ctx* c);
+int vrt_fields_init_tables(vrt_ctx* c);
+int vrt_split_init_tables(vrt_ctx* c);
+
+static std::string g_err;
+
+namespace {
+
+__global__ void k_set_params(VrtStepParams* p, VrtStepParams v) { *p = v; }
+__global__ void k_fill(double* a, long n, double v) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = v;
+}
+
+int dev_alloc(vrt_ctx* c, std::vector<double*>& pool, double** out, size_t n_doubles) {
+    double* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(n_doubles, 1) * sizeof(double));
+    if (e != cudaSuccess) { c->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return VRT_ERR_NOMEM; }
+    e = cudaMemsetAsync(p, 0, std::max<size_t>(n_doubles, 1) * sizeof(double), c->stream);
+    if (e != cudaSuccess) { c->err = std::string("cudaMemset: ") + cudaGetErrorString(e); return VRT_ERR_CUDA; }
+    pool.push_back(p);
+    *out = p;
+    return 0;
+}
+
+void free_species(VrtSpeciesState& S) {
+    for (double* p : S.allocations) cudaFree(p);
+    S.allocations.clear();
+    if (S.d_patches) { cudaFree(S.d_patches); S.d_patches = nullptr; }
+    S.patches.clear(); S.level_patches.clear(); S.desc.clear();
+    S.configured = false;
+}
+
+void drop_graphs(vrt_ctx* c) {
+    for (int k = 0; k < 3; k++) if (c->graph_step3[k]) { cudaGraphExecDestroy(c->graph_step3[k]); c->graph_step3[k] = nullptr; }
+    if (c->graph_fields) { cudaGraphExecDestroy(c->graph_fields); c->graph_fields = nullptr; }
+}
+
+bool check(vrt_ctx* c, bool ok, const char* msg) { if (!ok) c->err = msg; return ok; }
+
+int set_params_async(vrt_ctx* c, double dt, const double* laser) {
+    VrtStepParams v{}; v.dt = dt;
+    if (laser) std::memcpy(v.laser, laser, sizeof(v.laser));
+    k_set_params<<<1, 1, 0, c->stream>>>(c->d_params, v);
+    VRT_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vrt_global_error(void) { return g_err.c_str(); }
+const char* vrt_last_error(const vrt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+const char* vrt_version(void) { return "veritas_b200 0.1 (sm_100a)"; }
+
+int vrt_create(vrt_ctx** out, int device, int n_species) {
+    if (!out || n_species < 1 || n_species > 8) { g_err = "vrt_create: bad arguments"; return VRT_ERR_ARG; }
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        g_err = std::string("vrt_create: no CUDA device (") + cudaGetErrorString(e) + "); veritas_b200 has no CPU fallback";
+        return VRT_ERR_CUDA;
+    }
+    if (device < 0 || device >= n_dev) { g_err = "vrt_create: device ordinal out of range"; return VRT_ERR_ARG; }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { g_err = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return VRT_ERR_CUDA; }
+    vrt_ctx* c = new vrt_ctx();
+    c->device = device; c->n_species = n_species; c->S.resize(n_species);
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_params, sizeof(VrtStepParams));
+    if (e == cudaSuccess) e = cudaMemset(c->d_params, 0, sizeof(VrtStepParams));
+    if (e != cudaSuccess) { g_err = std::string("vrt_create: ") + cudaGetErrorString(e); delete c; return VRT_ERR_CUDA; }
+    if (vrt_fields_init_tables(c) || vrt_split_init_tables(c)) { g_err = "vrt_create: " + c->err; delete c; return VRT_ERR_CUDA; }
+    *out = c;
+    return 0;
+}
+
+int vrt_destroy(vrt_ctx* c) {
+    if (!c) return VRT_ERR_ARG;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    drop_graphs(c);
+    vrt_comm_destroy(c);
+    for (auto& S : c->S) { free_species(S); if (S.d_charges) cudaFree(S.d_charges); }
+    for (double* p : c->field_allocs) cudaFree(p);
+    if (c->d_params) cudaFree(c->d_params);
+    if (c->d_comm) cudaFree(c->d_comm);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+int vrt_sync(vrt_ctx* c) {
+    if (!c) return VRT_ERR_ARG;
+    VRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+void* vrt_stream(vrt_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int vrt_set_grid(vrt_ctx* c, int N, double dx, int pre, int post, int r, int max_depth) {
+    if (!c) return VRT_ERR_ARG;
+    if (!check(c, N >= 8 && dx > 0 && pre >= 2 && post >= 2 && r >= 2 && max_depth >= 0, "vrt_set_grid: bad arguments")) return VRT_ERR_ARG;
+    if (!check(c, !c->grid_set, "vrt_set_grid: grid already set")) return VRT_ERR_STATE;
+    cudaSetDevice(c->device);
+    VrtFields& F = c->F;
+    F.N = N; F.pre = pre; F.post = post; F.M = N + pre + post; F.dx = dx;
+    c->refinement_ratio = r; c->max_depth = max_depth;
+    int rc;
+    for (int v = 0; v < 6; v++) if ((rc = dev_alloc(c, c->field_allocs, &F.Y[v], 8L * F.M))) return rc;
+    if ((rc = dev_alloc(c, c->field_allocs, &F.a_squared, N + 1))) return rc;
+    if ((rc = dev_alloc(c, c->field_allocs, &F.a_squared0, N + 1))) return rc;
+    if ((rc = dev_alloc(c, c->field_allocs, &F.PHI, N))) return rc;
+    if ((rc = dev_alloc(c, c->field_allocs, &F.E, N + 4))) return rc;
+    if ((rc = dev_alloc(c, c->field_allocs, &F.E0, N + 4))) return rc;
+    if ((rc = dev_alloc(c, c->field_allocs, &F.charge, N))) return rc;
+    if ((rc = dev_alloc(c, c->field_allocs, &F.J, N))) return rc;
+    if ((rc = dev_alloc(c, c->field_allocs, &F.neutral, N))) return rc;
+    if ((rc = dev_alloc(c, c->field_allocs, &F.Ex0, 2))) return rc;
+    if ((rc = dev_alloc(c, c->field_allocs, &F.scratch, 4L * N))) return rc;
+    if ((rc = dev_alloc(c, c->field_allocs, &F.cfl, 2))) return rc;
+    for (auto& S : c->S) { double* p; if ((rc = dev_alloc(c, c->field_allocs, &p, N))) return rc; S.d_charges = p; c->field_allocs.pop_back(); }
+    c->x_begin = 0; c->x_end = N;
+    c->grid_set = true;
+    return 0;
+}
+
+int vrt_set_species(vrt_ctx* c, int s, double mass, double charge, double pmin, double dp_finest) {
+    if (!c) return VRT_ERR_ARG;
+    if (!check(c, s >= 0 && s < c->n_species && mass > 0 && dp_finest > 0, "vrt_set_species: bad arguments")) return VRT_ERR_ARG;
+    c->S[s].sp = VrtSpecies{mass, charge, pmin, dp_finest};
+    c->S[s].configured = true;
+    return 0;
+}
+
+int vrt_set_path(vrt_ctx* c, int path) {
+    if (!c || path < VRT_PATH_AUTO || path > VRT_PATH_FUSED) return VRT_ERR_ARG;
+    c->requested_path = path;
+    return 0;
+}
+int vrt_get_path(vrt_ctx* c, int s) { return (c && s >= 0 && s < c->n_species) ? c->S[s].path : VRT_ERR_ARG; }
+
+int vrt_set_slab(vrt_ctx* c, int rank, int n_ranks, int x_begin, int x_end) {
+    if (!c) return VRT_ERR_ARG;
+    if (!check(c, c->grid_set, "vrt_set_slab: call vrt_set_grid first")) return VRT_ERR_STATE;
+    if (!check(c, n_ranks >= 1 && rank >= 0 && rank < n_ranks && x_begin >= 0 && x_end <= c->F.N && x_end - x_begin >= 8,
+               "vrt_set_slab: bad arguments")) return VRT_ERR_ARG;
+    if (!check(c, n_ranks == 1 || ((x_end - x_begin) * n_ranks == c->F.N && x_begin == rank * (x_end - x_begin)),
+               "vrt_set_slab: slabs must be equal and ordered by rank")) return VRT_ERR_ARG;
+    for (auto& S : c->S) if (!check(c, S.desc.empty(), "vrt_set_slab: must precede vrt_set_hierarchy")) return VRT_ERR_STATE;
+    c->rank = rank; c->n_ranks = n_ranks; c->x_begin = x_begin; c->x_end = x_end;
+    return 0;
+}
+
+int vrt_set_hierarchy(vrt_ctx* c, int s, int n_patches, const vrt_patch_desc* d) {
+    if (!c) return VRT_ERR_ARG;
+    if (!check(c, c->grid_set && s >= 0 && s < c->n_species && c->S[s].configured, "vrt_set_hierarchy: set grid and species first")) return VRT_ERR_STATE;
+    if (!check(c, n_patches >= 1 && d, "vrt_set_hierarchy: bad arguments")) return VRT_ERR_ARG;
+    cudaSetDevice(c->device);
+    VRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    drop_graphs(c);
+    VrtSpeciesState& S = c->S[s];
+    VrtSpecies sp = S.sp;
+    free_species(S);
+    S.sp = sp; S.configured = true;
+    const int r = c->refinement_ratio;
+    for (int p = 0; p < n_patches; p++) {
+        const vrt_patch_desc& q = d[p];
+        if (!check(c, q.depth >= 0 && q.depth <= c->max_depth && q.n_x >= 4 && q.n_p >= 4 && q.n_x % r == 0 && q.n_p % r == 0,
+                   "vrt_set_hierarchy: bad patch descriptor")) return VRT_ERR_ARG;
+    }
+    S.desc.assign(d, d + n_patches);
+    // path selection: the fused streaming kernel serves single-level full-domain patches (optionally x-slabs)
+    const vrt_patch_desc& q0 = d[0];
+    const bool full = (n_patches == 1 && c->max_depth == 0 && q0.depth == 0 && q0.x_pos == 0 && q0.p_pos == 0 && q0.n_x == c->F.N &&
+                       q0.up && q0.down && q0.left && q0.right);
+    int path = c->requested_path;
+    if (path == VRT_PATH_AUTO) path = full ? VRT_PATH_FUSED : VRT_PATH_SPLIT;
+    if (!check(c, path != VRT_PATH_FUSED || full, "vrt_set_hierarchy: the fused path needs one full-domain single-level patch")) return VRT_ERR_ARG;
+    if (!check(c, c->n_ranks == 1 || path == VRT_PATH_FUSED, "vrt_set_hierarchy: x-slabs need the fused path")) return VRT_ERR_ARG;
+    S.path = path;
+    int rc;
+    if (path == VRT_PATH_FUSED) {
+        VrtSlabDev& L = S.slab;
+        L = VrtSlabDev{};
+        L.n_x = c->x_end - c->x_begin; L.n_p = q0.n_p; L.x_begin = c->x_begin; L.n_x_global = c->F.N;
+        L.left = (c->x_begin == 0); L.right = (c->x_end == c->F.N);
+        L.gx = 3; L.pitch = ((q0.n_p + 8 + 3) / 4) * 4;
+        L.plane = (long)(L.n_x + 2 * L.gx) * L.pitch;
+        L.dx = c->F.dx; L.dp = sp.dp_finest;
+        for (int k = 0; k < 3; k++) if ((rc = dev_alloc(c, S.allocations, &L.f[k], L.plane))) return rc;
+        for (int k = 0; k < 5; k++) {
+            if ((rc = dev_alloc(c, S.allocations, &L.FxH[k], L.plane))) return rc;
+            if ((rc = dev_alloc(c, S.allocations, &L.FpH[k], L.plane))) return rc;
+        }
+        if ((rc = dev_alloc(c, S.allocations, &L.chargeR, L.n_x))) return rc;
+        if ((rc = dev_alloc(c, S.allocations, &L.currentR, L.n_x))) return rc;
+        S.i_f0 = S.i_f1 = 0;
+        return 0;
+    }
+    // split path: SoA planes per patch, reference layout
+    S.level_patches.assign(c->max_depth + 1, {});
+    std::vector<int> order(n_patches);
+    for (int p = 0; p < n_patches; p++) order[p] = p;
+    // the device table is grouped by depth so that one level is a contiguous range; S.patches is indexed by
+    // the caller's patch number, table_index maps it into the table
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return d[a].depth < d[b].depth; });
+    S.patches.resize(n_patches);
+    std::vector<VrtPatchDev> table(n_patches);
+    S.table_index.assign(n_patches, 0);
+    for (int ti = 0; ti < n_patches; ti++) {
+        const int p = order[ti];
+        const vrt_patch_desc& q = d[p];
+        VrtPatchDev P{};
+        P.n_x = q.n_x; P.n_p = q.n_p; P.x_pos = q.x_pos; P.p_pos = q.p_pos;
+        P.up = q.up; P.down = q.down; P.left = q.left; P.right = q.right; P.depth = q.depth;
+        P.rtb = (int)std::lround(std::pow((double)r, q.depth));
+        P.pitch = q.n_p + 4; P.npad = (long)(q.n_x + 4) * (q.n_p + 4);
+        P.dx = std::pow((double)r, (double)q.depth) * c->F.dx;              // Settings::GetDx (Settings.cpp:142-144)
+        P.dp = std::pow((double)r, (double)q.depth) * sp.dp_finest;         // Settings::GetDp (Settings.cpp:138-140)
+        double** planes[] = {&P.f0, &P.f1, &P.f2, &P.fx, &P.fp, &P.ex, &P.ep, &P.FxL, &P.FpL, &P.FxLS, &P.FpLS, &P.FxDS, &P.FpDS, &P.Rp, &P.Rm, &P.Cx, &P.Cp};
+        for (double** pl : planes) if ((rc = dev_alloc(c, S.allocations, pl, P.npad))) return rc;
+        if ((rc = dev_alloc(c, S.allocations, &P.FxH, 6 * P.npad))) return rc;
+        if ((rc = dev_alloc(c, S.allocations, &P.FpH, 6 * P.npad))) return rc;
+        if ((rc = dev_alloc(c, S.allocations, &P.chargeR, (long)P.n_x * P.rtb))) return rc;
+        if ((rc = dev_alloc(c, S.allocations, &P.currentR, (long)P.n_x * P.rtb))) return rc;
+        S.patches[p] = P; table[ti] = P; S.table_index[p] = ti;
+        S.level_patches[q.depth].push_back(ti);
+    }
+    S.table = table;
+    VRT_CUDA(c, cudaMalloc(&S.d_patches, sizeof(VrtPatchDev) * n_patches));
+    VRT_CUDA(c, cudaMemcpyAsync(S.d_patches, S.table.data(), sizeof(VrtPatchDev) * n_patches, cudaMemcpyHostToDevice, c->stream));
+    VRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- data movement ----------------------------------------------------------------------------------
+static int slab_plane_index(const VrtSpeciesState& S, int state) {
+    if (state == 0) return S.i_f0;
+    if (state == 1) return S.i_f1;
+    return -1;
+}
+
+int vrt_patch_upload_f(vrt_ctx* c, int s, int patch, int state, const double* host) {
+    if (!c || !host) return VRT_ERR_ARG;
+    if (!check(c, s >= 0 && s < c->n_species && patch >= 0 && patch < (int)c->S[s].desc.size() && state >= 0 && state <= 2, "vrt_patch_upload_f: bad arguments")) return VRT_ERR_ARG;
+    cudaSetDevice(c->device);
+    VrtSpeciesState& S = c->S[s];
+    if (S.path == VRT_PATH_FUSED) {
+        if (!check(c, state != 2, "vrt_patch_upload_f: the fused path keeps no predictor state")) return VRT_ERR_ARG;
+        VrtSlabDev& L = S.slab;
+        // uploading state 1 while both states alias one plane splits them
+        if (state == 1 && S.i_f1 == S.i_f0) {
+            S.i_f1 = (S.i_f0 + 1) % 3;
+        }
+        int pi = slab_plane_index(S, state);
+        // host: (n_xg+4) x (n_p+4), cell (i,j) at (n_p+4)*(i+2)+2+j.  device column c (local) <- host column x_begin+c.
+        // halo columns inside the global domain come from the host array; beyond its 2 ghost columns they stay 0.
+        const int hp = L.n_p + 4;
+        for (int cl = -L.gx; cl < L.n_x + L.gx; cl++) {
+            int gi = L.x_begin + cl;
+            if (gi < -2 || gi >= L.n_x_global + 2) continue;
+            VRT_CUDA(c, cudaMemcpyAsync(L.f[pi] + (long)(cl + L.gx) * L.pitch + 2, host + (long)(gi + 2) * hp, sizeof(double) * hp,
+                                        cudaMemcpyHostToDevice, c->stream));
+        }
+        VRT_CUDA(c, cudaStreamSynchronize(c->stream));
+        return 0;
+    }
+    VrtPatchDev& P = S.patches[patch];
+    double* dst = state == 0 ? P.f0 : (state == 1 ? P.f1 : P.f2);
+    VRT_CUDA(c, cudaMemcpyAsync(dst, host, sizeof(double) * P.npad, cudaMemcpyHostToDevice, c->stream));
+    VRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int vrt_patch_download_f(vrt_ctx* c, int s, int patch, int state, double* host) {
+    if (!c || !host) return VRT_ERR_ARG;
+    if (!check(c, s >= 0 && s < c->n_species && patch >= 0 && patch < (int)c->S[s].desc.size() && state >= 0 && state <= 2, "vrt_patch_download_f: bad arguments")) return VRT_ERR_ARG;
+    cudaSetDevice(c->device);
+    VrtSpeciesState& S = c->S[s];
+    if (S.path == VRT_PATH_FUSED) {
+        if (!check(c, state != 2, "vrt_patch_download_f: the fused path keeps no predictor state")) return VRT_ERR_ARG;
+        VrtSlabDev& L = S.slab;
+        int pi = slab_plane_index(S, state);
+        const int hp = L.n_p + 4;
+        // only this slab's own columns (plus the physical ghost columns it touches) are written to the host array
+        int lo = L.left ? -2 : 0, hi = L.right ? L.n_x + 2 : L.n_x;
+        VRT_CUDA(c, cudaMemcpy2DAsync(host + (long)(L.x_begin + lo + 2) * hp, sizeof(double) * hp,
+                                      L.f[pi] + (long)(lo + L.gx) * L.pitch + 2, sizeof(double) * L.pitch, sizeof(double) * hp, hi - lo,
+                                      cudaMemcpyDeviceToHost, c->stream));
+        VRT_CUDA(c, cudaStreamSynchronize(c->stream));
+        return 0;
+    }
+    VrtPatchDev& P = S.patches[patch];
+    const double* src = state == 0 ? P.f0 : (state == 1 ? P.f1 : P.f2);
+    VRT_CUDA(c, cudaMemcpyAsync(host, src, sizeof(double) * P.npad, cudaMemcpyDeviceToHost, c->stream));
+    VRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int vrt_commit_state(vrt_ctx* c, int s) {
+    if (!c || s < 0 || s >= c->n_species) return VRT_ERR_ARG;
+    cudaSetDevice(c->device);
+    VrtSpeciesState& S = c->S[s];
+    if (S.path == VRT_PATH_FUSED) { S.i_f0 = S.i_f1; return 0; }
+    for (size_t d = 0; d < S.level_patches.size(); d++)
+        if (int r = vrt_split_substep(c, s, (int)d, &c->d_params->dt, 5, 3)) return r;
+    return 0;
+}
+
+int vrt_field_upload(vrt_ctx* c, int which, int slot, const double* host) {
+    if (!c || !host || which < 0 || which > 5 || slot < 0 || slot > 7 || !c->grid_set) return VRT_ERR_ARG;
+    cudaSetDevice(c->device);
+    VRT_CUDA(c, cudaMemcpyAsync(c->F.Y[which] + (long)slot * c->F.M, host, sizeof(double) * c->F.M, cudaMemcpyHostToDevice, c->stream));
+    VRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int vrt_field_download(vrt_ctx* c, int which, int slot, double* host) {
+    if (!c || !host || which < 0 || which > 5 || slot < 0 || slot > 7 || !c->grid_set) return VRT_ERR_ARG;
+    cudaSetDevice(c->device);
+    VRT_CUDA(c, cudaMemcpyAsync(host, c->F.Y[which] + (long)slot * c->F.M, sizeof(double) * c->F.M, cudaMemcpyDeviceToHost, c->stream));
+    VRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static double* sel_1d(vrt_ctx* c, int which, long* n) {
+    VrtFields& F = c->F;
+    *n = F.N;
+    switch (which) {
+        case VRT_PHI: return F.PHI;
+        case VRT_CHARGE: return F.charge;
+        case VRT_J: return F.J;
+        case VRT_A_SQUARED: *n = F.N + 1; return F.a_squared;
+        case VRT_NEUTRALIZATION: return F.neutral;
+        case VRT_EFIELD: return F.E + 2;
+        default:
+            if (which >= VRT_CHARGES0 && which < VRT_CHARGES0 + c->n_species) return c->S[which - VRT_CHARGES0].d_charges;
+    }
+    return nullptr;
+}
+int vrt_set_1d(vrt_ctx* c, int which, const double* host) {
+    if (!c || !host || !c->grid_set) return VRT_ERR_ARG;
+    cudaSetDevice(c->device);
+    long n; double* d = sel_1d(c, which, &n);
+    if (!check(c, d != nullptr && which != VRT_EFIELD, "vrt_set_1d: bad selector")) return VRT_ERR_ARG;
+    VRT_CUDA(c, cudaMemcpyAsync(d, host, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    VRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (which == VRT_PHI) return vrt_fields_refresh_efield(c);
+    return 0;
+}
+int vrt_get_1d(vrt_ctx* c, int which, double* host) {
+    if (!c || !host || !c->grid_set) return VRT_ERR_ARG;
+    cudaSetDevice(c->device);
+    long n; double* d = sel_1d(c, which, &n);
+    if (!check(c, d != nullptr, "vrt_get_1d: bad selector")) return VRT_ERR_ARG;
+    VRT_CUDA(c, cudaMemcpyAsync(host, d, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    VRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int vrt_set_scalar(vrt_ctx* c, int which, double v) {
+    if (!c || !c->grid_set) return VRT_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (which == VRT_TIME) { c->time = v; return 0; }
+    if (which == VRT_EX0) {
+        k_fill<<<1, 1, 0, c->stream>>>(c->F.Ex0, 1, v);
+        VRT_CUDA(c, cudaGetLastError());
+        return vrt_fields_refresh_efield(c);
+    }
+    return VRT_ERR_ARG;
+}
+int vrt_get_scalar(vrt_ctx* c, int which, double* v) {
+    if (!c || !v || !c->grid_set) return VRT_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (which == VRT_TIME) { *v = c->time; return 0; }
+    if (which == VRT_EX0) {
+        VRT_CUDA(c, cudaMemcpyAsync(v, c->F.Ex0, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        VRT_CUDA(c, cudaStreamSynchronize(c->stream));
+        return 0;
+    }
+    return VRT_ERR_ARG;
+}
+
+// ---- hot path ---------------------------------------------------------------------------------------
+static int ready(vrt_ctx* c) {
+    if (!c) return VRT_ERR_ARG;
+    if (!c->grid_set) { c->err = "grid not set"; return VRT_ERR_STATE; }
+    for (auto& S : c->S) if (S.desc.empty()) { c->err = "hierarchy not set for every species"; return VRT_ERR_STATE; }
+    cudaSetDevice(c->device);
+    return 0;
+}
+
+static int moments_impl(vrt_ctx* c) {
+    int r;
+    if ((r = vrt_fields_assemble_begin(c))) return r;
+    for (int s = 0; s < c->n_species; s++) {
+        r = (c->S[s].path == VRT_PATH_FUSED) ? vrt_fused_moments(c, s) : vrt_split_moments(c, s);
+        if (r) return r;
+    }
+    if (c->n_ranks > 1 && (r = vrt_comm_gather_moments(c))) return r;
+    return vrt_fields_assemble_end(c);
+}
+
+int vrt_moments(vrt_ctx* c) { if (int r = ready(c)) return r; return moments_impl(c); }
+
+int vrt_enforce_neutralization(vrt_ctx* c) {
+    if (int r = ready(c)) return r;
+    if (int r = moments_impl(c)) return r;
+    return vrt_fields_neutralize(c);
+}
+
+int vrt_poisson(vrt_ctx* c) { if (int r = ready(c)) return r; return vrt_fields_poisson(c); }
+
+static int push_data_impl(vrt_ctx* c, int s, int val) {
+    VrtSpeciesState& S = c->S[s];
+    if (S.path == VRT_PATH_FUSED) return 0;   // ghosts of the slab planes are never written; halos are exchanged per stage
+    // Mesh::PushData (Mesh.cpp:91-106).  Single-level hierarchies: every neighbour is the BoundaryCondition object.
+    if (!check(c, c->max_depth == 0 || S.desc.size() == 1, "vrt_push_data: multi-patch hierarchies are not supported yet")) return VRT_ERR_STATE;
+    for (size_t d = 0; d < S.level_patches.size(); d++)
+        if (int r = vrt_split_fill_domain_ghosts(c, s, (int)d, val)) return r;
+    return 0;
+}
+
+static int vlasov_stage_impl(vrt_ctx* c, int s, const double* d_dt, int step) {
+    VrtSpeciesState& S = c->S[s];
+    int r;
+    if (S.path == VRT_PATH_FUSED) {
+        if ((r = vrt_fused_stage(c, s, d_dt, step))) return r;
+        if (c->n_ranks > 1 && (r = vrt_comm_halo_exchange(c, s))) return r;
+        return 0;
+    }
+    const int nl = (int)S.level_patches.size();
+    for (int d = nl - 1; d >= 0; d--) if ((r = vrt_split_substep(c, s, d, d_dt, step, 0))) return r;
+    if ((r = push_data_impl(c, s, 2))) return r;
+    for (int d = nl - 1; d >= 0; d--) if ((r = vrt_split_substep(c, s, d, d_dt, step, 1))) return r;
+    // Mesh::PushBoundaryC: zero-trip loops when every neighbour is the BoundaryCondition object (quirk Q8)
+    for (int d = nl - 1; d >= 0; d--) if ((r = vrt_split_substep(c, s, d, d_dt, step, 2))) return r;
+    if ((r = push_data_impl(c, s, 1))) return r;
+    if (step == 5) for (int d = nl - 1; d >= 0; d--) if ((r = vrt_split_substep(c, s, d, d_dt, step, 3))) return r;
+    return 0;
+}
+
+int vrt_vlasov_stage(vrt_ctx* c, int s, double dt, int step) {
+    if (int r = ready(c)) return r;
+    if (!check(c, s >= 0 && s < c->n_species && step >= 0 && step <= 5, "vrt_vlasov_stage: bad arguments")) return VRT_ERR_ARG;
+    if (int r = set_params_async(c, dt, nullptr)) return r;
+    if (step == 0) if (int r = vrt_fields_snapshot_stage0(c)) return r;
+    return vlasov_stage_impl(c, s, &c->d_params->dt, step);
+}
+
+int vrt_vlasov_substep(vrt_ctx* c, int s, int depth, double dt, int step, int substep) {
+    if (int r = ready(c)) return r;
+    if (!check(c, s >= 0 && s < c->n_species && step >= -1 && step <= 5, "vrt_vlasov_substep: bad arguments")) return VRT_ERR_ARG;
+    if (!check(c, c->S[s].path == VRT_PATH_SPLIT, "vrt_vlasov_substep: sub-steps exist on the split path only (vrt_set_path)")) return VRT_ERR_STATE;
+    if (int r = set_params_async(c, dt, nullptr)) return r;
+    return vrt_split_substep(c, s, depth, &c->d_params->dt, step < 0 ? 0 : step, substep);
+}
+
+int vrt_push_data(vrt_ctx* c, int s, int val) {
+    if (int r = ready(c)) return r;
+    if (!check(c, s >= 0 && s < c->n_species && (val == 1 || val == 2), "vrt_push_data: bad arguments")) return VRT_ERR_ARG;
+    return push_data_impl(c, s, val);
+}
+int vrt_push_boundary_c(vrt_ctx* c, int s) {
+    if (int r = ready(c)) return r;
+    if (!check(c, s >= 0 && s < c->n_species, "vrt_push_boundary_c: bad arguments")) return VRT_ERR_ARG;
+    return 0;   // single-patch levels: all limiter-sync loops have zero trip count (quirk Q8)
+}
+
+int vrt_field_stage(vrt_ctx* c, int step, double dt, double by0, double bz0) {
+    if (!c || !c->grid_set) return VRT_ERR_ARG;
+    if (!check(c, step >= 0 && step <= 5, "vrt_field_stage: bad step")) return VRT_ERR_ARG;
+    cudaSetDevice(c->device);
+    double laser[12] = {0};
+    laser[2 * step] = by0; laser[2 * step + 1] = bz0;
+    if (int r = set_params_async(c, dt, laser)) return r;
+    return vrt_fields_rhs_update_faces(c, step, c->d_params);
+}
+
+int vrt_cfl_bound(vrt_ctx* c, double* out) {
+    if (!c || !out || !c->grid_set) return VRT_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (int r = vrt_fields_cfl(c)) return r;
+    VRT_CUDA(c, cudaMemcpyAsync(out, c->F.cfl + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    VRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+double vrt_update_time(double time, int step, double dt) {   // Settings::UpdateTime (Settings.cpp:166-179)
+    if (step == 1) time += (0.5 * dt);
+    else if (step == 2) time += (0.332 - 0.5) * dt;
+    else if (step == 3) time += (0.62 - 0.332) * dt;
+    else if (step == 4) time += (0.85 - 0.62) * dt;
+    else if (step == 5) time += (1.0 - 0.85) * dt;
+    return time;
+}
+
+// the six stages of SolverManager::Advance as stream work (SolverManager.cpp:28-39)
+static int enqueue_step(vrt_ctx* c) {
+    int r;
+    for (int i = 0; i < 6; i++) {
+        if ((r = moments_impl(c))) return r;
+        if ((r = vrt_fields_poisson(c))) return r;
+        if (i == 0 && (r = vrt_fields_snapshot_stage0(c))) return r;
+        for (int s = 0; s < c->n_species; s++) if ((r = vlasov_stage_impl(c, s, &c->d_params->dt, i))) return r;
+        if ((r = vrt_fields_rhs_update_faces(c, i, c->d_params))) return r;
+    }
+    return 0;
+}
+
+int vrt_step(vrt_ctx* c, double dt, const double laser[12]) {
+    if (int r = ready(c)) return r;
+    if (!check(c, laser != nullptr, "vrt_step: laser values missing")) return VRT_ERR_ARG;
+    if (int r = set_params_async(c, dt, laser)) return r;
+    const long l0 = c->launches;
+    // The plane rotation of the fused path has period 2 after the first step; graphs are cached per rotation state.
+    int key = 0;
+    bool any_fused = false;
+    for (auto& S : c->S) if (S.path == VRT_PATH_FUSED) { any_fused = true; key = S.i_f0; if (!check(c, S.i_f0 == S.i_f1, "vrt_step: mid-step state")) return VRT_ERR_STATE; }
+    for (auto& S : c->S) if (S.path == VRT_PATH_FUSED && !check(c, S.i_f0 == key, "vrt_step: species out of phase")) return VRT_ERR_STATE;
+    (void)any_fused;
+    const bool use_graph = c->use_graph && c->n_ranks == 1;
+    if (!use_graph) {
+        if (int r = enqueue_step(c)) return r;
+        c->last_step_launches = c->launches - l0;
+    } else {
+        if (!c->graph_step3[key]) {
+            std::vector<std::pair<int, int>> saved;
+            for (auto& S : c->S) saved.push_back({S.i_f0, S.i_f1});
+            VRT_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            int r = enqueue_step(c);
+            cudaGraph_t g = nullptr;
+            cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+            c->graph_launches[key] = c->launches - l0;
+            for (size_t s = 0; s < c->S.size(); s++) { c->graph_end_state[key][s] = {c->S[s].i_f0, c->S[s].i_f1}; c->S[s].i_f0 = saved[s].first; c->S[s].i_f1 = saved[s].second; }
+            if (r) { if (g) cudaGraphDestroy(g); return r; }
+            if (e != cudaSuccess) { c->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e); return VRT_ERR_CUDA; }
+            e = cudaGraphInstantiate(&c->graph_step3[key], g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) { c->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e); return VRT_ERR_CUDA; }
+        }
+        VRT_CUDA(c, cudaGraphLaunch(c->graph_step3[key], c->stream));
+        for (size_t s = 0; s < c->S.size(); s++) { c->S[s].i_f0 = c->graph_end_state[key][s].first; c->S[s].i_f1 = c->graph_end_state[key][s].second; }
+        c->last_step_launches = c->graph_launches[key];
+    }
+    for (int i = 0; i < 6; i++) c->time = vrt_update_time(c->time, i, dt);
+    return 0;
+}
+
+int vrt_step_fields(vrt_ctx* c, double dt, const double laser[12]) {
+    if (!c || !c->grid_set || !laser) return VRT_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (int r = set_params_async(c, dt, laser)) return r;
+    const long l0 = c->launches;
+    for (int i = 0; i < 6; i++) if (int r = vrt_fields_rhs_update_faces(c, i, c->d_params)) return r;
+    c->last_step_launches = c->launches - l0;
+    for (int i = 0; i < 6; i++) c->time = vrt_update_time(c->time, i, dt);
+    return 0;
+}
+
+long vrt_last_step_launches(const vrt_ctx* c) { return c ? c->last_step_launches : 0; }
+
+int vrt_set_option(vrt_ctx* c, int option, int value) {
+    if (!c) return VRT_ERR_ARG;
+    if (option == 0) { c->use_graph = value != 0; return 0; }
+    return VRT_ERR_ARG;
+}
+
+int vrt_init_maxwellian_slab(vrt_ctx* c, int s, double xl, double xr, double n0, double T, int quadrature_depth) {
+    if (int r = ready(c)) return r;
+    if (!check(c, s >= 0 && s < c->n_species, "vrt_init_maxwellian_slab: bad species")) return VRT_ERR_ARG;
+    return vrt_init_kernels_maxwellian(c, s, xl, xr, n0, T, quadrature_depth);
+}
+
+}  // extern "C"

@@ -1,0 +1,97 @@
+// Multi-GPU x-slab plumbing (no counterpart in the reference): per-stage exchange of the 3-column
+// f halo between x-neighbours (grouped ncclSend/ncclRecv, walls have one neighbour) and the in-place all-gather of
+// the per-slab charge/current moments so that every rank runs the 1-D Poisson + Maxwell solve redundantly.
+// NCCL is bound at run time (dlopen) so that single-GPU use needs no NCCL at all and a host process that already
+// loaded a libnccl (e.g. torch's) shares it.
+#include "vrt_internal.cuh"
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace {
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+} g_nccl;
+
+bool load_nccl(std::string* err) {
+    if (g_nccl.h) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) { g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.h) break; }
+    if (!g_nccl.h) { *err = std::string("dlopen(libnccl.so.2): ") + dlerror(); return false; }
+#define SYM(field, name) *(void**)(&g_nccl.field) = dlsym(g_nccl.h, name); if (!g_nccl.field) { *err = std::string("dlsym ") + name; return false; }
+    SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+    SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(AllGather, "ncclAllGather") SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    return true;
+}
+}  // namespace
+
+#define VRT_NCCL(ctx, call)                                                                   \
+    do {                                                                                      \
+        ncclResult_t r_ = (call);                                                             \
+        if (r_ != ncclSuccess) { (ctx)->err = std::string(#call) + ": " + g_nccl.GetErrorString(r_); return VRT_ERR_NCCL; } \
+    } while (0)
+
+extern "C" int vrt_nccl_unique_id(void* out128) {
+    std::string err;
+    if (!out128 || !load_nccl(&err)) return VRT_ERR_NCCL;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    return g_nccl.GetUniqueId((ncclUniqueId*)out128) == ncclSuccess ? 0 : VRT_ERR_NCCL;
+}
+
+extern "C" int vrt_comm_init(vrt_ctx* c, const void* unique_id128, int rank, int n_ranks) {
+    if (!c || !unique_id128) return VRT_ERR_ARG;
+    if (rank != c->rank || n_ranks != c->n_ranks) { c->err = "vrt_comm_init: rank/n_ranks differ from vrt_set_slab"; return VRT_ERR_ARG; }
+    if (!load_nccl(&c->err)) return VRT_ERR_NCCL;
+    cudaSetDevice(c->device);
+    ncclUniqueId id; memcpy(&id, unique_id128, sizeof(id));
+    ncclComm_t comm;
+    VRT_NCCL(c, g_nccl.CommInitRank(&comm, n_ranks, id, rank));
+    c->nccl_comm = comm;
+    return 0;
+}
+
+int vrt_comm_halo_exchange(vrt_ctx* c, int s) {
+    if (!c->nccl_comm) { c->err = "multi-rank context without vrt_comm_init"; return VRT_ERR_STATE; }
+    VrtSpeciesState& S = c->S[s];
+    VrtSlabDev& L = S.slab;
+    ncclComm_t comm = (ncclComm_t)c->nccl_comm;
+    double* f = L.f[S.i_f1];
+    const size_t n = (size_t)L.gx * L.pitch;
+    VRT_NCCL(c, g_nccl.GroupStart());
+    if (c->rank > 0) {
+        VRT_NCCL(c, g_nccl.Send(f + (long)L.gx * L.pitch, n, ncclDouble, c->rank - 1, comm, c->stream));        // own columns [0,3)
+        VRT_NCCL(c, g_nccl.Recv(f, n, ncclDouble, c->rank - 1, comm, c->stream));                               // halo [-3,0)
+    }
+    if (c->rank < c->n_ranks - 1) {
+        VRT_NCCL(c, g_nccl.Send(f + (long)L.n_x * L.pitch, n, ncclDouble, c->rank + 1, comm, c->stream));       // own [n_x-3,n_x)
+        VRT_NCCL(c, g_nccl.Recv(f + (long)(L.n_x + L.gx) * L.pitch, n, ncclDouble, c->rank + 1, comm, c->stream));   // halo [n_x,n_x+3)
+    }
+    VRT_NCCL(c, g_nccl.GroupEnd());
+    return 0;
+}
+
+int vrt_comm_gather_moments(vrt_ctx* c) {
+    if (!c->nccl_comm) { c->err = "multi-rank context without vrt_comm_init"; return VRT_ERR_STATE; }
+    ncclComm_t comm = (ncclComm_t)c->nccl_comm;
+    const size_t n = (size_t)(c->x_end - c->x_begin);
+    VRT_NCCL(c, g_nccl.GroupStart());
+    for (int s = 0; s < c->n_species; s++)
+        VRT_NCCL(c, g_nccl.AllGather(c->S[s].d_charges + c->x_begin, c->S[s].d_charges, n, ncclDouble, comm, c->stream));
+    VRT_NCCL(c, g_nccl.AllGather(c->F.J + c->x_begin, c->F.J, n, ncclDouble, comm, c->stream));
+    VRT_NCCL(c, g_nccl.GroupEnd());
+    return 0;
+}
+
+void vrt_comm_destroy(vrt_ctx* c) {
+    if (c->nccl_comm && g_nccl.CommDestroy) { g_nccl.CommDestroy((ncclComm_t)c->nccl_comm); c->nccl_comm = nullptr; }
+}

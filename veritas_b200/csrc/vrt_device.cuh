@@ -1,0 +1,49 @@
+// Device helpers shared by the split and fused Vlasov kernels.  The speed/gamma chain uses explicit
+// round-to-nearest intrinsics so that it is never FMA-contracted.
+#pragma once
+#include "vrt_internal.cuh"
+
+struct Sp { double m, q, pmin, m_inv; };
+
+__device__ __forceinline__ long NS(const VrtPatchDev& P, int i, int j) { return (long)P.pitch * (i + 2) + 2 + j; }
+// Rectangle::Momentum (Rectangle.hpp:86-88)
+__device__ __forceinline__ double momentum(const VrtPatchDev& P, const Sp& sp, double i) {
+    return __dadd_rn(sp.pmin, __dmul_rn(P.dp, __dadd_rn(i, (double)P.p_pos)));
+}
+// Rectangle::Gamma (Rectangle.hpp:181-183)
+__device__ __forceinline__ double gamma_(const Sp& sp, double p, double a2) {
+    double k = __dmul_rn(__dmul_rn(sp.m_inv, VRT_C_INV), __dmul_rn(sp.m_inv, VRT_C_INV));
+    return __dsqrt_rn(__dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(p, p), a2), k)));
+}
+__device__ __forceinline__ int finest_index(const VrtPatchDev& P, int i) { return (int)((double)P.rtb * (double)(i + P.x_pos)); }
+__device__ __forceinline__ double a_sq(const VrtFields& F, int i) { return F.a_squared[min(max(i, 0), F.N)]; }
+// Rectangle::GetEfield (Rectangle.cpp:1055-1067) on the tabulated EMFieldSolver::GetEfield
+__device__ __forceinline__ double patch_efield(const VrtPatchDev& P, const VrtFields& F, int i) {
+    int j = finest_index(P, i);
+    double t = 0.0;
+    for (int k = 0; k < P.rtb; k++) t += F.E[j + k + 2];
+    t *= (1.0 / (double)P.rtb);
+    return t;
+}
+__device__ __forceinline__ double vmax(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double vmin(double a, double b) { return a < b ? a : b; }
+
+// Rectangle::GetWenoEdgeValueNoMax (Rectangle.cpp:980-1030)
+__device__ __forceinline__ double weno(double f1, double f2, double f3, double f4, bool right) {
+    double fL = (1.0 / 6) * (-f1 + 5 * f2 + 2 * f3);
+    double fR = (1.0 / 6) * (2 * f2 + 5 * f3 - f4);
+    double AL = f1 - 2 * f2 + f3, BL = f3 - f1;
+    double AR = f2 - 2 * f3 + f4, BR = f4 - f2;
+    double bL = 4.0 / 3 * (AL * AL) + 0.5 * AL * BL + 0.25 * (BL * BL);
+    double bR = 4.0 / 3 * (AR * AR) - 0.5 * AR * BR + 0.25 * (BR * BR);
+    double mm = 1.0e-10;
+    double oL = 0.5 / ((mm + bL) * (mm + bL));
+    double oR = 0.5 / ((mm + bR) * (mm + bR));
+    double wL = oL / (oL + oR), wR = oR / (oL + oR);
+    double wL0 = wL * (0.75 + wL * (wL - 0.5));
+    double wR0 = wR * (0.75 + wR * (wR - 0.5));
+    double W = right ? ((wL0 > wR0) ? wL0 : wR0) : ((wL0 < wR0) ? wL0 : wR0);
+    double a = W / (wL0 + wR0);
+    return a * fL + (1 - a) * fR;
+}
+

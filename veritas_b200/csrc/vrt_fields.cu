@@ -1,0 +1,341 @@
+// 1-D field solver on the device: EMFieldSolver of the reference (/root/reference/EMSolver.cpp).
+// Compiled with -fmad=false: a_squared feeds Gamma(), whose rounding decides the upwind direction of the
+// p~0 row, so every expression keeps the reference's operation order without contraction.
+#include "vrt_internal.cuh"
+
+namespace {
+
+__constant__ VrtTableau c_tab;
+
+// ---- RGKCalculateRHS (EMSolver.cpp:479-553) ---------------------------------------------------------
+__global__ void k_field_rhs(VrtFields F, int step, const VrtStepParams* prm) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int M = F.M, N = F.N, pre = F.pre, post = F.post;
+    if (i >= M) return;
+    const double *By = F.Y[VRT_BY] + M, *Bz = F.Y[VRT_BZ] + M, *Ey = F.Y[VRT_EY] + M, *Ez = F.Y[VRT_EZ] + M,
+                 *Ay = F.Y[VRT_AY] + M, *Az = F.Y[VRT_AZ] + M;   // slot 1
+    const long s2 = (long)(step + 2) * M + i;
+    const double dx_inv = 1 / F.dx;
+    double rBy = 0, rBz = 0, rEy = 0, rEz = 0, rAy = 0, rAz = 0;
+    if (i == 0) {
+        double by0 = prm->laser[2 * step], bz0 = prm->laser[2 * step + 1];
+        rBy = dx_inv * (Ez[i + 1] - Ez[i]);
+        rBz = -dx_inv * (Ey[i + 1] - Ey[i]);
+        rEy = -dx_inv * (Bz[i] - bz0) * VRT_EPS0_INV * VRT_MU_INV;
+        rEz = dx_inv * (By[i] - by0) * VRT_EPS0_INV * VRT_MU_INV;
+        rAy = -Ey[i]; rAz = -Ez[i];
+    } else if (i < pre || (i >= pre + N && i < pre + N + post - 2)) {
+        rBy = dx_inv * (Ez[i + 1] - Ez[i]);
+        rBz = -dx_inv * (Ey[i + 1] - Ey[i]);
+        rEy = -dx_inv * (Bz[i] - Bz[i - 1]) * VRT_EPS0_INV * VRT_MU_INV;
+        rEz = dx_inv * (By[i] - By[i - 1]) * VRT_EPS0_INV * VRT_MU_INV;
+        rAy = -Ey[i]; rAz = -Ez[i];
+    } else if (i >= pre && i < pre + N) {
+        const double c1 = -1.0 / 24, c2 = 9.0 / 8.0;
+        double Jv = F.J[i - pre];
+        rBy = dx_inv * (c1 * (Ez[i + 2] - Ez[i - 1]) + c2 * (Ez[i + 1] - Ez[i]));
+        rBz = -dx_inv * (c1 * (Ey[i + 2] - Ey[i - 1]) + c2 * (Ey[i + 1] - Ey[i]));
+        rEy = -dx_inv * (c1 * (Bz[i + 1] - Bz[i - 2]) + c2 * (Bz[i] - Bz[i - 1])) * VRT_EPS0_INV * VRT_MU_INV - VRT_EPS0_INV * Jv * Ay[i];
+        rEz = dx_inv * (c1 * (By[i + 1] - By[i - 2]) + c2 * (By[i] - By[i - 1])) * VRT_EPS0_INV * VRT_MU_INV - VRT_EPS0_INV * Jv * Az[i];
+        rAy = -Ey[i]; rAz = -Ez[i];
+    }   // last two cells stay 0
+    F.Y[VRT_BY][s2] = rBy; F.Y[VRT_BZ][s2] = rBz; F.Y[VRT_EY][s2] = rEy;
+    F.Y[VRT_EZ][s2] = rEz; F.Y[VRT_AY][s2] = rAy; F.Y[VRT_AZ][s2] = rAz;
+}
+
+// ---- RGKUpdateIntermediateSolution (EMSolver.cpp:204-338) --------------------------------------------
+__global__ void k_field_update(VrtFields F, int step, const VrtStepParams* prm) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int M = F.M;
+    if (i >= M) return;
+    const double timestep = prm->dt;
+    double* y = F.Y[blockIdx.y];
+    if (step < 5) {
+        double s = y[i] + (c_tab.a[step][0] * timestep) * y[2L * M + i];
+        for (int k = 1; k <= step; k++) s = s + (c_tab.a[step][k] * timestep) * y[(long)(2 + k) * M + i];
+        y[M + i] = s;
+    } else {
+        double s = y[M + i];
+        for (int k = 0; k < 6; k++) {
+            double ak = (k < 5) ? c_tab.a[4][k] * timestep : 0.0;
+            double bk = c_tab.a[5][k] * timestep - ak;
+            s = s + bk * y[(long)(2 + k) * M + i];
+        }
+        y[i] = s; y[M + i] = s;
+    }
+}
+
+__device__ __forceinline__ double weno_unbiased(double f1, double f2, double f3, double f4) {   // EMSolver.cpp:565-585
+    double fL = (1.0 / 6) * (-f1 + 5 * f2 + 2 * f3), fR = (1.0 / 6) * (2 * f2 + 5 * f3 - f4);
+    double AL = f1 - 2 * f2 + f3, BL = f3 - f1, AR = f2 - 2 * f3 + f4, BR = f4 - f2;
+    double bL = 4.0 / 3 * (AL * AL) + 0.5 * AL * BL + 0.25 * (BL * BL);
+    double bR = 4.0 / 3 * (AR * AR) - 0.5 * AR * BR + 0.25 * (BR * BR);
+    double mm = 1.0e-10;
+    double oL = 0.5 / ((mm + bL) * (mm + bL)), oR = 0.5 / ((mm + bR) * (mm + bR));
+    double wL = oL / (oL + oR), wR = oR / (oL + oR);
+    return wL * fL + wR * fR;
+}
+// ---- InterpolateToFaces (EMSolver.cpp:555-619) -------------------------------------------------------
+__global__ void k_field_faces(VrtFields F) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F.N) return;
+    const double *Ay = F.Y[VRT_AY] + F.M + F.pre + i, *Az = F.Y[VRT_AZ] + F.M + F.pre + i;
+    double ay = weno_unbiased(Ay[-2], Ay[-1], Ay[0], Ay[1]);
+    double az = weno_unbiased(Az[-2], Az[-1], Az[0], Az[1]);
+    F.a_squared[i] = (ay * ay) + (az * az);
+}
+
+// ---- UpdatePotential (EMSolver.cpp:156-192) ----------------------------------------------------------
+// The reference solves  A x = b  with A = the dense matrix of EMSolver.cpp:28-67 as LAPACK (column-major) sees it:
+// column 0 = e_0, column c>0 = the periodic 4th-order -d2 stencil (w = 1/12, -4/3, 5/2, -4/3, 1/12) centred on
+// row c.  Hence x_0 = sum(b) and x_{r>0} = y_r where  L y = b - sum(b) e_0, y_0 = 0, L the periodic stencil
+// operator.  L factors exactly as  T D  with  T = periodic tridiag(-1/12, 7/6, -1/12)  and  D = periodic
+// tridiag(-1, 2, -1).  T^-1 is a convolution with C rho^|k| (rho = 7 - sqrt(48), C = 6/sqrt(48)); rho^18 < 3e-21,
+// so 17 terms per side are exact to fp64.  D y = z with y_0 = 0 is two running sums.  O(N), no N x N matrix.
+constexpr int PK = 17;
+constexpr int PT = 1024;
+
+__device__ double block_sum(double v, double* sh) {
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) sh[32] = t;
+    }
+    __syncthreads();
+    return sh[32];
+}
+// exclusive prefix over the per-thread totals of a block; returns the offset for this thread
+__device__ double block_excl_scan(double v, double* sh, double* total) {
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double inc = v;
+    for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) sh[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        double t = lane < (blockDim.x >> 5) ? sh[lane] : 0.0, ti = t;
+        for (int o = 1; o < 32; o <<= 1) { double u = __shfl_up_sync(0xffffffffu, ti, o); if (lane >= o) ti += u; }
+        sh[lane] = ti - t;               // exclusive warp offsets
+        if (lane == 31) sh[32] = ti;     // block total
+    }
+    __syncthreads();
+    *total = sh[32];
+    return sh[w] + (inc - v);
+}
+
+__global__ void __launch_bounds__(PT) k_poisson(VrtFields F) {
+    __shared__ double sh[40];
+    __shared__ double green[PK + 1];
+    const int N = F.N, tid = threadIdx.x;
+    double* b = F.scratch;          // rhs, then b'
+    double* z = F.scratch + N;      // T^-1 b'
+    double* cpre = F.scratch + 2L * N;
+    if (tid <= PK) {
+        const double rho = 1.0 / (7.0 + sqrt(48.0)), Cg = 6.0 / sqrt(48.0);   // rho = 7 - sqrt(48) without cancellation
+        double g = Cg;
+        for (int k = 0; k < tid; k++) g *= rho;
+        green[tid] = g;
+    }
+    const double te = VRT_EPS0_INV, w = F.dx * F.dx;
+    const int per = (N + PT - 1) / PT, lo = tid * per, hi = min(N, lo + per);
+    double s = 0.0;
+    for (int i = lo; i < hi; i++) { double v = te * (F.charge[i] + F.neutral[i]); v *= w; b[i] = v; s += v; }
+    const double sb = block_sum(s, sh);
+    if (tid == 0) b[0] -= sb;
+    __syncthreads();
+    // z = T^-1 b'  (strided so that neighbouring threads read neighbouring entries)
+    for (int i = tid; i < N; i += PT) {
+        double acc = green[0] * b[i];
+        for (int k = 1; k <= PK; k++) {
+            int ip = (i + k) % N;
+            int im = (((i - k) % N) + N) % N;
+            acc += green[k] * (b[ip] + b[im]);
+        }
+        z[i] = acc;
+    }
+    __syncthreads();
+    // c_i = inclusive prefix of z
+    double loc = 0.0;
+    for (int i = lo; i < hi; i++) loc += z[i];
+    double tot;
+    double off = block_excl_scan(loc, sh, &tot);
+    double run = off, csum = 0.0;
+    for (int i = lo; i < hi; i++) { run += z[i]; cpre[i] = run; csum += run; }
+    const double cmean = block_sum(csum, sh) / (double)N;
+    // y_i = sum_{k<i} (cmean - c_k)
+    loc = 0.0;
+    for (int i = lo; i < hi; i++) loc += (cmean - cpre[i]);
+    off = block_excl_scan(loc, sh, &tot);
+    run = off;
+    for (int i = lo; i < hi; i++) { double d = cmean - cpre[i]; F.PHI[i] = (i == 0) ? sb : run; run += d; }
+}
+
+// EMFieldSolver::GetEfield without the Ex0 term (EMSolver.cpp:137-154)
+__device__ __forceinline__ double efield_base(const VrtFields& F, int i) {
+    const int N = F.N;
+    int ip1 = i + 1, im1 = i - 1, ip2 = i + 2, im2 = i - 2;
+    ip1 = ip1 > -1 ? ip1 : ip1 + N; im1 = im1 > -1 ? im1 : im1 + N;
+    ip2 = ip2 > -1 ? ip2 : ip2 + N; im2 = im2 > -1 ? im2 : im2 + N;
+    ip1 = ip1 < N ? ip1 : ip1 - N; im1 = im1 < N ? im1 : im1 - N;
+    ip2 = ip2 < N ? ip2 : ip2 - N; im2 = im2 < N ? im2 : im2 - N;
+    const double fieldCoef = 1.0 / (12 * F.dx);
+    return -fieldCoef * (8 * (F.PHI[ip1] - F.PHI[im1]) - F.PHI[ip2] + F.PHI[im2]);
+}
+// Ex0 += -(GetEfield(-1)+GetEfield(0))*0.5 (EMSolver.cpp:191, quirk Q4), then tabulate E on [-2, N+1]
+__global__ void k_efield(VrtFields F, int update_ex0) {
+    __shared__ double ex0_new;
+    if (threadIdx.x == 0) {
+        double ex0 = *F.Ex0;
+        if (update_ex0) ex0 += -((efield_base(F, -1) + ex0) + (efield_base(F, 0) + ex0)) * 0.5;
+        ex0_new = ex0;
+    }
+    __syncthreads();
+    int i = blockIdx.x * blockDim.x + threadIdx.x - 2;
+    if (i <= F.N + 1) F.E[i + 2] = efield_base(F, i) + ex0_new;
+    if (blockIdx.x == 0 && threadIdx.x == 0) F.Ex0[1] = ex0_new;   // staged; committed by k_commit_ex0
+}
+__global__ void k_commit_ex0(VrtFields F) { F.Ex0[0] = F.Ex0[1]; }
+
+// ---- EstimateCFLBound (EMSolver.cpp:631-664), un-offset indexing kept (quirk Q3) ---------------------
+struct CflSpecies { int n; double m[8], q[8], dps[8]; double dpsMax; };
+__global__ void k_cfl(VrtFields F, CflSpecies sp) {
+    __shared__ double sh[32];
+    double pc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < F.N; i += gridDim.x * blockDim.x) {
+        double Azv = F.Y[VRT_AZ][i], Ayv = F.Y[VRT_AY][i];
+        double As = Ayv * Ayv + Azv * Azv, t = 0.0;
+        for (int j = 0; j < sp.n; j++) t = fmax(t, fabs(sp.q[j]) / sp.m[j] / sqrt(1 + As / ((sp.m[j] * VRT_CS) * (sp.m[j] * VRT_CS))) * sp.dps[j]);
+        pc = fmax(pc, t * fabs(Ayv * F.Y[VRT_BZ][i] - Azv * F.Y[VRT_BY][i]) + sp.dpsMax * fabs(F.E[i + 2]));
+    }
+    for (int o = 16; o > 0; o >>= 1) pc = fmax(pc, __shfl_down_sync(0xffffffffu, pc, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = pc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) t = fmax(t, __shfl_down_sync(0xffffffffu, t, o));
+        // pc >= 0: the IEEE bit pattern is monotone, so an integer max is exact
+        if (threadIdx.x == 0) atomicMax((unsigned long long*)F.cfl, (unsigned long long)__double_as_longlong(t));
+    }
+}
+__global__ void k_cfl_finish(VrtFields F) { double pc = *F.cfl; F.cfl[1] = 1.0 / fmax((VRT_CS / F.dx + pc), 1e-40); }
+
+// ---- AssembleRhoAndJ bookkeeping (EMSolver.cpp:104-122, Level.cpp:19-62) -----------------------------
+__global__ void k_zero2(double* a, double* b, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { a[i] = 0.0; if (b) b[i] = 0.0; }
+}
+// charges[s][x0+i] (+)= chargeR[i]; J[x0+i] += currentR[i]
+__global__ void k_add_moments(double* charges, double* J, const double* chargeR, const double* currentR, int x0, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { charges[x0 + i] += chargeR[i]; J[x0 + i] += currentR[i]; }
+}
+__global__ void k_add1(double* dst, const double* src, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += src[i];
+}
+__global__ void k_neutralize(VrtFields F) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < F.N) { F.J[i] = 0.0; F.neutral[i] = -F.charge[i]; }
+}
+__global__ void k_copy(double* dst, const double* src, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
+bool g_tab_loaded = false;
+inline int grid1(int n, int b = 256) { return (n + b - 1) / b; }
+
+}  // namespace
+
+int vrt_fields_init_tables(vrt_ctx* c) {
+    if (!g_tab_loaded) { VRT_CUDA(c, cudaMemcpyToSymbol(c_tab, &kTableau, sizeof(VrtTableau))); g_tab_loaded = true; }
+    return 0;
+}
+
+int vrt_fields_rhs_update_faces(vrt_ctx* c, int step, const VrtStepParams* d_params) {
+    VrtFields& F = c->F;
+    k_field_rhs<<<grid1(F.M), 256, 0, c->stream>>>(F, step, d_params);
+    k_field_update<<<dim3(grid1(F.M), 6), 256, 0, c->stream>>>(F, step, d_params);
+    k_field_faces<<<grid1(F.N), 256, 0, c->stream>>>(F);
+    c->launches += 3;
+    VRT_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+int vrt_fields_poisson(vrt_ctx* c) {
+    VrtFields& F = c->F;
+    k_poisson<<<1, PT, 0, c->stream>>>(F);
+    k_efield<<<grid1(F.N + 4), 256, 0, c->stream>>>(F, 1);
+    k_commit_ex0<<<1, 1, 0, c->stream>>>(F);
+    c->launches += 3;
+    VRT_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+// recompute the E table from the current PHI and Ex0 (after uploads)
+int vrt_fields_refresh_efield(vrt_ctx* c) {
+    VrtFields& F = c->F;
+    k_efield<<<grid1(F.N + 4), 256, 0, c->stream>>>(F, 0);
+    c->launches += 1;
+    VRT_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+int vrt_fields_cfl(vrt_ctx* c) {
+    VrtFields& F = c->F;
+    CflSpecies sp{}; sp.n = c->n_species; sp.dpsMax = 0.0;
+    for (int i = 0; i < c->n_species; i++) {
+        sp.m[i] = c->S[i].sp.m; sp.q[i] = c->S[i].sp.q; sp.dps[i] = 1 / c->S[i].sp.dp_finest;
+        sp.dpsMax = fmax(sp.dpsMax, fabs(sp.q[i]) * sp.dps[i]);
+    }
+    VRT_CUDA(c, cudaMemsetAsync(F.cfl, 0, 2 * sizeof(double), c->stream));
+    k_cfl<<<min(grid1(F.N), 148 * 4), 256, 0, c->stream>>>(F, sp);
+    k_cfl_finish<<<1, 1, 0, c->stream>>>(F);
+    c->launches += 2;
+    VRT_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+int vrt_fields_assemble_begin(vrt_ctx* c) {
+    VrtFields& F = c->F;
+    k_zero2<<<grid1(F.N), 256, 0, c->stream>>>(F.charge, F.J, F.N);
+    c->launches += 1;
+    for (int s = 0; s < c->n_species; s++) {
+        k_zero2<<<grid1(F.N), 256, 0, c->stream>>>(c->S[s].d_charges, nullptr, F.N);
+        c->launches += 1;
+    }
+    VRT_CUDA(c, cudaGetLastError());
+    return 0;
+}
+int vrt_fields_assemble_add(vrt_ctx* c, int s, const double* chargeR, const double* currentR, int x0, int n) {
+    k_add_moments<<<grid1(n), 256, 0, c->stream>>>(c->S[s].d_charges, c->F.J, chargeR, currentR, x0, n);
+    c->launches += 1;
+    VRT_CUDA(c, cudaGetLastError());
+    return 0;
+}
+int vrt_fields_assemble_end(vrt_ctx* c) {
+    for (int s = 0; s < c->n_species; s++) {
+        k_add1<<<grid1(c->F.N), 256, 0, c->stream>>>(c->F.charge, c->S[s].d_charges, c->F.N);
+        c->launches += 1;
+    }
+    VRT_CUDA(c, cudaGetLastError());
+    return 0;
+}
+int vrt_fields_snapshot_stage0(vrt_ctx* c) {
+    VrtFields& F = c->F;
+    k_copy<<<grid1(F.N + 1), 256, 0, c->stream>>>(F.a_squared0, F.a_squared, F.N + 1);
+    k_copy<<<grid1(F.N + 4), 256, 0, c->stream>>>(F.E0, F.E, F.N + 4);
+    c->launches += 2;
+    VRT_CUDA(c, cudaGetLastError());
+    return 0;
+}
+int vrt_fields_neutralize(vrt_ctx* c) {
+    k_neutralize<<<grid1(c->F.N), 256, 0, c->stream>>>(c->F);
+    c->launches += 1;
+    VRT_CUDA(c, cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,150 @@
+// veritas_b200 internal declarations shared by the CUDA translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <utility>
+#include <vector>
+#include "../../include/veritas_b200.h"
+
+#define VRT_EPS0_INV 1.1294e+11     // veritas.hpp:22 (reference literals, quirk Q9)
+#define VRT_MU_INV 795774.715482    // veritas.hpp:25
+#define VRT_CS 299792458.0          // veritas.hpp:26
+#define VRT_C_INV 3.33564095e-9     // veritas.hpp:27
+
+// RK tableau, literal values of Rectangle.cpp:1397-1498 / EMSolver.cpp:210-312 (row s = stage s, row 5 = b)
+struct VrtTableau { double a[6][6]; };
+static const VrtTableau kTableau = {{{0.5, 0, 0, 0, 0, 0},
+                                     {0.221776, 0.110224, 0, 0, 0, 0},
+                                     {-0.04884659515311857, -0.17772065232640102, 0.8465672474795197, 0, 0, 0},
+                                     {-0.15541685842491548, -0.3567050098221991, 1.0587258798684427, 0.30339598837867193, 0, 0},
+                                     {0.2014243506726763, 0.008742057842904185, 0.15993995707168115, 0.4038290605220775, 0.22606457389066084, 0},
+                                     {0.15791629516167136, 0.0, 0.18675894052400077, 0.6805652953093346, -0.27524053099500667, 0.25}}};
+
+// Per-step parameters living in device memory so that a captured CUDA graph can be replayed with new values:
+// written by one cudaMemcpyAsync from pinned host memory before the graph launch.
+struct VrtStepParams {
+    double dt;
+    double laser[12];   // by0,bz0 per stage
+};
+
+// 1-D field-solver state on the device (EMFieldSolver members, EMSolver.hpp:10-23)
+struct VrtFields {
+    int N, pre, post, M;        // x_size_finest, n_prepad, n_postpad, M = N+pre+post
+    double dx;                  // finest dx
+    double* Y[6];               // By,Bz,Ey,Ez,Ay,Az: 8 slots x M, slot-major (Index(i,s) = s*M+i)
+    double* a_squared;          // N+1 (x-faces; entry N never written, quirk Q2)
+    double* a_squared0;         // stage-0 snapshot (fused path: low-order flux recompute, quirk Q1)
+    double* PHI;                // N
+    double* E;                  // N+4: E[i+2] = EMFieldSolver::GetEfield(i), i in [-2, N+1]
+    double* E0;                 // stage-0 snapshot of E
+    double* charge; double* J; double* neutral;   // N each
+    double* Ex0;                // device scalar
+    double* scratch;            // Poisson workspace, 4*N
+    double* cfl;                // device scalar (max-reduction result)
+};
+
+// Species constants (Settings.hpp:39-41)
+struct VrtSpecies {
+    double m, q, pmin, dp_finest;
+};
+
+// One Rectangle on the device, split path: SoA planes in the reference's padded layout.
+struct VrtPatchDev {
+    int n_x, n_p, x_pos, p_pos, up, down, left, right, rtb, depth;
+    int pitch;                   // n_p + 4
+    long npad;                   // (n_x+4)*(n_p+4)
+    double dx, dp;
+    double *f0, *f1, *f2, *fx, *fp, *ex, *ep;
+    double *FxH, *FpH;           // 6 planes each, slot-major
+    double *FxL, *FpL;           // slot 0 (quirk Q1)
+    double *FxLS, *FpLS, *FxDS, *FpDS, *Rp, *Rm, *Cx, *Cp;
+    double *chargeR, *currentR;  // n_x*rtb each
+};
+
+// Fused-path storage of one full-domain (or x-slab) single-level patch: three rotating f planes and five
+// stored high-order flux pairs.  Rows are x columns (slow), p is contiguous.  GX ghost columns per side.
+struct VrtSlabDev {
+    int n_x, n_p;                // local interior columns, p cells
+    int x_begin;                 // global finest index of local column 0
+    int n_x_global;
+    int left, right;             // this slab touches the physical x boundary
+    int gx;                      // ghost columns per side (3)
+    int pitch;                   // doubles per column (n_p + 4 rounded up)
+    long plane;                  // doubles per plane = (n_x + 2*gx) * pitch
+    double dx, dp;
+    double* f[3];                // rotating: cur0 = f^n, cur1 = stage value, spare
+    double* FxH[5]; double* FpH[5];
+    double *chargeR, *currentR;  // n_x each
+};
+
+struct VrtSpeciesState {
+    VrtSpecies sp;
+    bool configured = false;
+    int path = VRT_PATH_SPLIT;
+    std::vector<vrt_patch_desc> desc;
+    // split path
+    std::vector<VrtPatchDev> patches;    // host copy of the descriptors (device pointers inside), caller's numbering
+    std::vector<VrtPatchDev> table;      // the same, grouped by depth = order of the device table
+    std::vector<int> table_index;        // caller's patch number -> table index
+    VrtPatchDev* d_patches = nullptr;    // device copy of `table`
+    std::vector<double*> allocations;
+    std::vector<std::vector<int>> level_patches;   // table indices per depth (contiguous ranges)
+    // fused path
+    VrtSlabDev slab;
+    int i_f0 = 0, i_f1 = 0;              // indices into slab.f: f^n and current stage value
+    double* d_charges = nullptr;         // per-species charge on the finest grid (N)
+};
+
+struct vrt_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int n_species = 0;
+    int refinement_ratio = 2, max_depth = 0;
+    bool grid_set = false;
+    VrtFields F{};
+    std::vector<double*> field_allocs;
+    std::vector<VrtSpeciesState> S;
+    int requested_path = VRT_PATH_AUTO;
+    double time = 0.0;
+    // slab decomposition
+    int rank = 0, n_ranks = 1, x_begin = 0, x_end = 0;
+    void* nccl_comm = nullptr;
+    // step graph
+    VrtStepParams* d_params = nullptr; VrtStepParams* h_params = nullptr;
+    cudaGraphExec_t graph_step3[3] = {nullptr, nullptr, nullptr};   // keyed by the plane-rotation state at step start
+    cudaGraphExec_t graph_fields = nullptr;
+    long graph_launches[3] = {0, 0, 0};
+    std::pair<int, int> graph_end_state[3][8];
+    bool use_graph = true;
+    long launches = 0, last_step_launches = 0;
+    double* d_comm = nullptr; long comm_doubles = 0;   // staging buffer for the moment all-gather
+};
+
+#define VRT_CUDA(ctx, call)                                                                      \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) {                                                                 \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                     \
+            return VRT_ERR_CUDA;                                                                 \
+        }                                                                                        \
+    } while (0)
+
+// ---- launchers implemented in the kernel translation units -----------------------------------------
+// split path (vrt_split.cu, compiled with -fmad=false)
+int vrt_split_substep(vrt_ctx* c, int s, int depth, const double* d_dt, int step, int substep);
+int vrt_split_fill_domain_ghosts(vrt_ctx* c, int s, int depth, int val);
+int vrt_split_moments(vrt_ctx* c, int s);
+// 1-D solver (vrt_fields.cu, compiled with -fmad=false)
+int vrt_fields_rhs_update_faces(vrt_ctx* c, int step, const VrtStepParams* d_params);
+int vrt_fields_poisson(vrt_ctx* c);
+int vrt_fields_cfl(vrt_ctx* c);
+int vrt_fields_assemble_begin(vrt_ctx* c);
+int vrt_fields_assemble_add(vrt_ctx* c, int s, const double* chargeR, const double* currentR, int x0, int n);
+int vrt_fields_assemble_end(vrt_ctx* c);
+int vrt_fields_snapshot_stage0(vrt_ctx* c);
+int vrt_fields_neutralize(vrt_ctx* c);
+// fused path (vrt_fused.cu)
+int vrt_fused_stage(vrt_ctx* c, int s, const double* d_dt, int step);
+int vrt_fused_moments(vrt_ctx* c, int s);
+int vrt_fused_zero_ghosts(vrt_ctx* c, int s, int plane_idx);

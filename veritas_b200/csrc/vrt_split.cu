@@ -1,0 +1,275 @@
+// Split path: Rectangle::FCTTimeStep sub-steps as separate kernels over the patches of one level, with the
+// reference's loop bounds, so that ghost/limiter syncs can run between them exactly as Mesh::Advance orders
+// them (Mesh.cpp:64-89).  Works for any hierarchy; one launch per level and sub-step through a
+// patch-descriptor table (blockIdx.y = patch).  Compiled with -fmad=false: bit-compatible with the
+// reference's non-FMA build in everything except libm log and the p-reduction order of the moments.
+#include "vrt_internal.cuh"
+#include "vrt_device.cuh"
+#include <algorithm>
+
+namespace {
+
+__constant__ VrtTableau c_tabs;
+bool g_tabs_loaded = false;
+
+#define PATCH_THREAD_SETUP                                                       \
+    const VrtPatchDev& P = patches[blockIdx.y];                                  \
+    long c = (long)blockIdx.x * blockDim.x + threadIdx.x;                        \
+    if (c >= P.npad) return;                                                     \
+    const int i = (int)(c / P.pitch) - 2, j = (int)(c % P.pitch) - 2;            \
+    const int nx = P.n_x, np = P.n_p; (void)nx; (void)np; (void)i; (void)j;
+
+// sub-step 0, part 1: advection speeds and WENO face values (Rectangle.cpp:1276-1312)
+__global__ void k_speeds_faces(const VrtPatchDev* patches, Sp sp, VrtFields F) {
+    PATCH_THREAD_SETUP
+    const double q = sp.q, dx_inv = 1 / P.dx, dp_inv = 1 / P.dp, cc = VRT_CS * VRT_CS * sp.m;
+    if (i >= -1 && i <= nx + 1 && j >= -1 && j <= np) {
+        double as = q * q * a_sq(F, finest_index(P, i));
+        double am = __dmul_rn(__dmul_rn(dp_inv, cc), __dadd_rn(gamma_(sp, momentum(P, sp, j + 1), as), -gamma_(sp, momentum(P, sp, j), as)));
+        P.ex[c] = am;
+        if (i >= 0 && i <= nx)
+            P.fx[c] = weno(P.f1[NS(P, i - 2, j)], P.f1[NS(P, i - 1, j)], P.f1[c], P.f1[NS(P, i + 1, j)], am > 0.0);
+    }
+    if (i >= -1 && i <= nx && j >= -1 && j <= np + 1) {
+        double as_1 = q * q * a_sq(F, finest_index(P, i));
+        double as_2 = q * q * a_sq(F, finest_index(P, i + 1));
+        double Em = q * patch_efield(P, F, i);
+        double mom = momentum(P, sp, j);
+        double am = __dadd_rn(Em, -__dmul_rn(__dmul_rn(cc, dx_inv), __dadd_rn(gamma_(sp, mom, as_2), -gamma_(sp, mom, as_1))));
+        P.ep[c] = am;
+        if (j >= 0 && j <= np)
+            P.fp[c] = weno(P.f1[c - 2], P.f1[c - 1], P.f1[c], P.f1[c + 1], am > 0.0);
+    }
+}
+
+// sub-step 0, part 2: high/low-order fluxes and the RK combination over the whole padded array
+// (Rectangle.cpp:1313-1517).  FxL/FpL hold slot 0 only (quirk Q1).
+__global__ void k_fluxes(const VrtPatchDev* patches, int step, const double* d_dt) {
+    PATCH_THREAD_SETUP
+    const double w3 = 1 / 48.0, dx_inv = 1 / P.dx, dp_inv = 1 / P.dp;
+    const double timestep = *d_dt;
+    double* FxHs = P.FxH + step * P.npad; double* FpHs = P.FpH + step * P.npad;
+    if (i >= 0 && i <= nx && j >= -1 && j <= np) {
+        double am = P.ex[c], ap1 = P.ex[c + 1], am1 = P.ex[c - 1];
+        double fm = P.fx[c], fp1 = P.fx[c + 1], fm1 = P.fx[c - 1];
+        FxHs[c] = dx_inv * (fm * am + w3 * (fp1 - fm1) * (ap1 - am1));
+        if (step == 0) P.FxL[c] = dx_inv * ((am > 0.0 ? P.f1[NS(P, i - 1, j)] : P.f1[c]) * am);
+    }
+    if (i >= -1 && i <= nx && j >= 0 && j <= np) {
+        long cp = c + P.pitch, cm = c - P.pitch;
+        double am = P.ep[c], ap1 = P.ep[cp], am1 = P.ep[cm];
+        double fm = P.fp[c], fp1 = P.fp[cp], fm1 = P.fp[cm];
+        FpHs[c] = dp_inv * (fm * am + w3 * (fp1 - fm1) * (ap1 - am1));
+        if (step == 0) P.FpL[c] = dp_inv * ((am > 0.0 ? P.f1[c - 1] : P.f1[c]) * am);
+    }
+    double a[6], aSum = 0.0;
+    for (int k = 0; k <= step; k++) { a[k] = c_tabs.a[step][k] * timestep; aSum = (k == 0) ? a[0] : aSum + a[k]; }
+    double xl = aSum * P.FxL[c], pl = aSum * P.FpL[c];
+    double sx = a[0] * P.FxH[c], sp_ = a[0] * P.FpH[c];
+    for (int k = 1; k <= step; k++) { sx = sx + a[k] * P.FxH[k * P.npad + c]; sp_ = sp_ + a[k] * P.FpH[k * P.npad + c]; }
+    P.FxLS[c] = xl; P.FpLS[c] = pl;
+    P.FxDS[c] = sx - xl; P.FpDS[c] = sp_ - pl;
+}
+
+// flux application in gather form, same summation order as the reference's serial scatter
+// (Rectangle.cpp:1518-1534 / 1595-1612; quirks Q11, Q14).  mode 0: f2 = f0 + FLS;  mode 1: f1 = f2 + C*FDS.
+__global__ void k_apply(const VrtPatchDev* patches, int mode) {
+    PATCH_THREAD_SETUP
+    if (i < 0 || i >= nx || j < 0 || j >= np) return;
+    const int xm = P.left ? 1 : 0, xp = P.right ? nx : nx + 1, pp = P.up ? np : np + 1, pm = P.down ? 1 : 0;
+    const long cxp = c + P.pitch;
+    const bool in_i = (i >= xm && i < xp), in_j = (j >= pm && j < pp);
+    const bool in_j1 = (j + 1 >= pm && j + 1 < pp), in_i1 = (i + 1 >= xm && i + 1 < xp);
+    double v;
+    if (mode == 0) {
+        v = P.f0[c];
+        if (in_i && in_j) { v += P.FxLS[c]; v += P.FpLS[c]; }
+        if (in_i && in_j1) v -= P.FpLS[c + 1];
+        if (in_i1 && in_j) v -= P.FxLS[cxp];
+        P.f2[c] = v;
+    } else {
+        v = P.f2[c];
+        if (in_i && in_j) { v += P.Cx[c] * P.FxDS[c]; v += P.Cp[c] * P.FpDS[c]; }
+        if (in_i && in_j1) v -= P.Cp[c + 1] * P.FpDS[c + 1];
+        if (in_i1 && in_j) v -= P.Cx[cxp] * P.FxDS[cxp];
+        P.f1[c] = v;
+    }
+}
+
+// sub-step 1: Zalesak ratios R+- on [-1,n_x]x[-1,n_p] (Rectangle.cpp:1536-1579)
+__global__ void k_limiter_r(const VrtPatchDev* patches) {
+    PATCH_THREAD_SETUP
+    if (i < -1 || i > nx || j < -1 || j > np) return;
+    const long cxp = c + P.pitch, cxm = c - P.pitch;
+    double Pp = vmax(0.0, P.FxDS[c]) - vmin(0.0, P.FxDS[cxp]) + vmax(0.0, P.FpDS[c]) - vmin(0.0, P.FpDS[c + 1]);
+    double Pm = vmax(0.0, P.FxDS[cxp]) - vmin(0.0, P.FxDS[c]) + vmax(0.0, P.FpDS[c + 1]) - vmin(0.0, P.FpDS[c]);
+    double w1a = vmax(P.f0[c], P.f2[c]), w2a = vmax(P.f0[cxp], P.f2[cxp]), w3a = vmax(P.f0[cxm], P.f2[cxm]);
+    double w4a = vmax(P.f0[c + 1], P.f2[c + 1]), w5a = vmax(P.f0[c - 1], P.f2[c - 1]);
+    double wMax = vmax(w1a, vmax(w2a, vmax(w3a, vmax(w4a, w5a))));
+    double w1i = vmin(P.f0[c], P.f2[c]), w2i = vmin(P.f0[cxp], P.f2[cxp]), w3i = vmin(P.f0[cxm], P.f2[cxm]);
+    double w4i = vmin(P.f0[c + 1], P.f2[c + 1]), w5i = vmin(P.f0[c - 1], P.f2[c - 1]);
+    double wMin = vmin(w1i, vmin(w2i, vmin(w3i, vmin(w4i, w5i))));
+    double Qm = -wMin + P.f2[c], Qp = wMax - P.f2[c];
+    P.Rp[c] = Pp > 0.0 ? vmin(1.0, Qp / Pp) : 0.0;
+    P.Rm[c] = Pm > 0.0 ? vmin(1.0, Qm / Pm) : 0.0;
+}
+// sub-step 1: limiter C, 1.0 everywhere then the interior loop i in [1,n_x), j in [0,n_p) (Rectangle.cpp:1581-1594, quirk Q13)
+__global__ void k_limiter_c(const VrtPatchDev* patches) {
+    PATCH_THREAD_SETUP
+    double cx = 1.0, cp = 1.0;
+    if (i >= 1 && i < nx && j >= 0 && j < np) {
+        long ci = c - P.pitch, cj = c - 1;
+        cx = P.FxDS[c] > 0.0 ? vmin(P.Rp[c], P.Rm[ci]) : vmin(P.Rp[ci], P.Rm[c]);
+        cp = P.FpDS[c] > 0.0 ? vmin(P.Rp[c], P.Rm[cj]) : vmin(P.Rp[cj], P.Rm[c]);
+    }
+    P.Cx[c] = cx; P.Cp[c] = cp;
+}
+// sub-step 3: f0 := f1 over the padded array (Rectangle.cpp:1614-1622)
+__global__ void k_commit(const VrtPatchDev* patches) {
+    PATCH_THREAD_SETUP
+    P.f0[c] = P.f1[c];
+}
+// Ghost fill when every neighbour is the physical boundary: BoundaryCondition::GetValueFromSameLevel == 0.0
+// (BoundaryCondition.cpp:6-8) through UpdateSameLevelBoundaries + UpdateCornerPoints (Rectangle.cpp:562-614, 1130-1214)
+__global__ void k_zero_ghosts(const VrtPatchDev* patches, int val) {
+    PATCH_THREAD_SETUP
+    if (i >= 0 && i < nx && j >= 0 && j < np) return;
+    double* f = val == 2 ? P.f2 : (val == 1 ? P.f1 : P.f0);
+    f[c] = 0.0;
+}
+
+// ---- moments: Rectangle::CalculateRhoAndJ, USINGMKL branch (Rectangle.cpp:157-282) -------------------------
+__constant__ double c_IM[12] = {0.104166666666667, -0.708333333333334, 0.708333333333334, -0.104166666666667,
+                                0.117647058823529, 0.029411764705882,  0.029411764705882, 0.117647058823529,
+                                -0.083333333333333, 0.166666666666667, -0.166666666666667, 0.083333333333334};
+// one sub-cell k of GetInterpolantsREL (Rectangle.cpp:139-155) plus the mean-preserving correction (198-205)
+__device__ double rel_value(const VrtPatchDev& P, int i, int j, int k) {
+    const int rtb = P.rtb;
+    double f1 = P.f1[NS(P, i - 2, j)], f2 = P.f1[NS(P, i - 1, j)], f3 = P.f1[NS(P, i, j)], f4 = P.f1[NS(P, i + 1, j)], f5 = P.f1[NS(P, i + 2, j)];
+    const double fc = f3;
+    f5 -= f3; f4 -= f3; f2 -= f3; f1 -= f3;
+    double a1 = c_IM[0] * f1 + c_IM[1] * f2 + c_IM[2] * f4 + c_IM[3] * f5;
+    double a2 = c_IM[4] * f1 + c_IM[5] * f2 + c_IM[6] * f4 + c_IM[7] * f5;
+    double a3 = c_IM[8] * f1 + c_IM[9] * f2 + c_IM[10] * f4 + c_IM[11] * f5;
+    double sum = 0.0, mine = 0.0;
+    for (int kk = 0; kk < rtb; kk++) {
+        double tl = -0.5 + kk / (double)rtb, tr = -0.5 + (kk + 1.0) / (double)rtb;
+        double c0 = (tl + tr) * 0.5;
+        double c1 = (tl * tl + tl * tr + tr * tr) / 3.0 - (1.0 / 12);
+        double c2 = (tl * tl * tl + tl * tl * tr + tl * tr * tr + tr * tr * tr) * 0.25;
+        double v = c0 * a1 + c1 * a2 + c2 * a3 + f3;
+        sum += v;
+        if (kk == k) mine = v;
+    }
+    double cor = fc - (1.0 / (double)rtb) * sum;
+    return mine + cor;
+}
+__device__ __forceinline__ double cell_a_sq(const VrtFields& F, int i) {   // EMSolver.hpp:56-63
+    i += F.pre; i = i > -1 ? i : 0; i = i < F.M ? i : F.M - 1;
+    double ay = F.Y[VRT_AY][F.M + i], az = F.Y[VRT_AZ][F.M + i];
+    return (ay * ay) + (az * az);
+}
+// grid: (n_x*rtb, patches); block reduces over p
+__global__ void __launch_bounds__(128) k_moments(const VrtPatchDev* patches, Sp sp, VrtFields F) {
+    const VrtPatchDev& P = patches[blockIdx.y];
+    const int rtb = P.rtb;
+    if ((int)blockIdx.x >= P.n_x * rtb) return;
+    const int i = blockIdx.x / rtb, k = blockIdx.x % rtb;
+    const double q = sp.q, c1 = sp.m_inv * VRT_C_INV, c2 = 1 / c1, c3 = 1 / 48.0;
+    const double a2 = q * q * cell_a_sq(F, (i + P.x_pos) * rtb + k);
+    double rho = 0.0, cur = 0.0;
+    for (int j = threadIdx.x; j < P.n_p; j += blockDim.x) {
+        double t0 = rel_value(P, i, j, k), tm1 = rel_value(P, i, j - 1, k), tp1 = rel_value(P, i, j + 1, k);
+        double pm1 = momentum(P, sp, j - 1), p0 = momentum(P, sp, j), p1 = momentum(P, sp, j + 1), p2 = momentum(P, sp, j + 2);
+        double um1 = gamma_(sp, pm1, a2) + c1 * pm1, u0 = gamma_(sp, p0, a2) + c1 * p0;
+        double u1 = gamma_(sp, p1, a2) + c1 * p1, u2 = gamma_(sp, p2, a2) + c1 * p2;
+        double gm = c2 * log(u1 / u0), gm1 = c2 * log(u0 / um1), gp1 = c2 * log(u2 / u1);
+        rho += t0;
+        cur += t0 * gm + c3 * (gp1 - gm1) * (tp1 - tm1);
+    }
+    __shared__ double sh[2][4];
+    for (int o = 16; o > 0; o >>= 1) { rho += __shfl_down_sync(0xffffffffu, rho, o); cur += __shfl_down_sync(0xffffffffu, cur, o); }
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = rho; sh[1][threadIdx.x >> 5] = cur; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        rho = (sh[0][0] + sh[0][1]) + (sh[0][2] + sh[0][3]);
+        cur = (sh[1][0] + sh[1][1]) + (sh[1][2] + sh[1][3]);
+        P.chargeR[blockIdx.x] = rho * (P.dp * q);
+        P.currentR[blockIdx.x] = cur * (-q * q / sp.m);
+    }
+}
+
+inline Sp make_sp(const VrtSpecies& s) { return Sp{s.m, s.q, s.pmin, 1 / s.m}; }
+
+}  // namespace
+
+int vrt_split_init_tables(vrt_ctx* c) {
+    if (!g_tabs_loaded) { VRT_CUDA(c, cudaMemcpyToSymbol(c_tabs, &kTableau, sizeof(VrtTableau))); g_tabs_loaded = true; }
+    return 0;
+}
+
+static bool level_grid(const VrtSpeciesState& S, int depth, dim3* grid, int* first) {
+    if (depth < 0 || depth >= (int)S.level_patches.size() || S.level_patches[depth].empty()) return false;
+    long mx = 0;
+    for (int p : S.level_patches[depth]) mx = std::max(mx, S.table[p].npad);
+    *first = S.level_patches[depth][0];   // patches of one level are contiguous in the table
+    *grid = dim3((unsigned)((mx + 255) / 256), (unsigned)S.level_patches[depth].size());
+    return true;
+}
+
+int vrt_split_substep(vrt_ctx* c, int s, int depth, const double* d_dt, int step, int substep) {
+    VrtSpeciesState& S = c->S[s];
+    dim3 grid; int first;
+    if (!level_grid(S, depth, &grid, &first)) return 0;
+    const VrtPatchDev* tab = S.d_patches + first;
+    Sp sp = make_sp(S.sp);
+    if (substep == 0) {
+        k_speeds_faces<<<grid, 256, 0, c->stream>>>(tab, sp, c->F);
+        k_fluxes<<<grid, 256, 0, c->stream>>>(tab, step, d_dt);
+        k_apply<<<grid, 256, 0, c->stream>>>(tab, 0);
+        c->launches += 3;
+    } else if (substep == 1) {
+        k_limiter_r<<<grid, 256, 0, c->stream>>>(tab);
+        k_limiter_c<<<grid, 256, 0, c->stream>>>(tab);
+        c->launches += 2;
+    } else if (substep == 2) {
+        k_apply<<<grid, 256, 0, c->stream>>>(tab, 1);
+        c->launches += 1;
+    } else if (substep == 3) {
+        k_commit<<<grid, 256, 0, c->stream>>>(tab);
+        c->launches += 1;
+    } else {
+        c->err = "vrt_vlasov_substep: substep must be 0..3";
+        return VRT_ERR_ARG;
+    }
+    VRT_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+int vrt_split_fill_domain_ghosts(vrt_ctx* c, int s, int depth, int val) {
+    VrtSpeciesState& S = c->S[s];
+    dim3 grid; int first;
+    if (!level_grid(S, depth, &grid, &first)) return 0;
+    k_zero_ghosts<<<grid, 256, 0, c->stream>>>(S.d_patches + first, val);
+    c->launches += 1;
+    VRT_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+int vrt_split_moments(vrt_ctx* c, int s) {
+    VrtSpeciesState& S = c->S[s];
+    Sp sp = make_sp(S.sp);
+    for (size_t d = 0; d < S.level_patches.size(); d++) {
+        if (S.level_patches[d].empty()) continue;
+        int first = S.level_patches[d][0], mx = 0;
+        for (int p : S.level_patches[d]) mx = std::max(mx, S.table[p].n_x * S.table[p].rtb);
+        k_moments<<<dim3(mx, (unsigned)S.level_patches[d].size()), 128, 0, c->stream>>>(S.d_patches + first, sp, c->F);
+        c->launches += 1;
+        VRT_CUDA(c, cudaGetLastError());
+        for (int p : S.level_patches[d]) {
+            const VrtPatchDev& P = S.table[p];
+            if (int r = vrt_fields_assemble_add(c, s, P.chargeR, P.currentR, P.x_pos * P.rtb, P.n_x * P.rtb)) return r;
+        }
+    }
+    return 0;
+}
