@@ -47,3 +47,40 @@ __device__ __forceinline__ double weno(double f1, double f2, double f3, double f
     return a * fL + (1 - a) * fR;
 }
 
+
+// ---- fused-path arithmetic helpers ---------------------------------------------------------------------------
+// reciprocal of a well-scaled operand (no denormal / inf / nan): MUFU.RCP64H seed + two Newton steps (< 1 ulp)
+__device__ __forceinline__ double rcp_scaled(double d) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    double e = fma(-d, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-d, x, 1.0);
+    x = fma(x, e, x);
+    return x;
+}
+// Rectangle::GetWenoEdgeValueNoMax (Rectangle.cpp:980-1030) with the five divisions folded into one.
+//   wL = oL/(oL+oR) = DR/(DL+DR),  D = (1e-10+b)^2;   wL0 = wL(0.75+wL(wL-0.5))  =>  wL0 (DL+DR)^3 = NL
+//   NL = DR (0.75 S^2 + DR^2 - 0.5 DR S),  NR likewise with DL;   W/(wL0+wR0) = sel(NL,NR)/(NL+NR)
+// DL, DR are first scaled by the power of two that brings S = DL+DR into [1,2) (exact), so S^3 cannot overflow.
+// Differs from the reference's evaluation order by a few ulp of the weights (continuous; SURVEY.md H2 allows it).
+__device__ __forceinline__ double weno_fast(double f1, double f2, double f3, double f4, bool right) {
+    const double fL = (1.0 / 6) * (-f1 + 5 * f2 + 2 * f3);
+    const double fR = (1.0 / 6) * (2 * f2 + 5 * f3 - f4);
+    const double AL = f1 - 2 * f2 + f3, BL = f3 - f1;
+    const double AR = f2 - 2 * f3 + f4, BR = f4 - f2;
+    const double bL = 4.0 / 3 * (AL * AL) + 0.5 * AL * BL + 0.25 * (BL * BL);
+    const double bR = 4.0 / 3 * (AR * AR) - 0.5 * AR * BR + 0.25 * (BR * BR);
+    const double mm = 1.0e-10;
+    const double DL = (mm + bL) * (mm + bL), DR = (mm + bR) * (mm + bR);
+    const double S = DL + DR;
+    const int e = min((__double2hiint(S) >> 20) & 0x7ff, 2045);
+    const double sc = __hiloint2double((2046 - e) << 20, 0);
+    const double dl = DL * sc, dr = DR * sc, ss = dl + dr;
+    const double h = 0.75 * ss;
+    const double NL = dr * fma(ss, fma(-0.5, dr, h), dr * dr);
+    const double NR = dl * fma(ss, fma(-0.5, dl, h), dl * dl);
+    const bool pickL = right ? (NL > NR) : (NL < NR);
+    const double a = (pickL ? NL : NR) * rcp_scaled(NL + NR);
+    return a * fL + (1 - a) * fR;
+}
