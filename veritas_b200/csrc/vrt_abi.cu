@@ -196,8 +196,10 @@ int vrt_set_hierarchy(vrt_ctx* c, int s, int n_patches, const vrt_patch_desc* d)
         L = VrtSlabDev{};
         L.n_x = c->x_end - c->x_begin; L.n_p = q0.n_p; L.x_begin = c->x_begin; L.n_x_global = c->F.N;
         L.left = (c->x_begin == 0); L.right = (c->x_end == c->F.N);
-        L.gx = 3; L.pitch = ((q0.n_p + 8 + 3) / 4) * 4;
-        L.plane = (long)(L.n_x + 2 * L.gx) * L.pitch;
+        // column layout: VRT_SLAB_GH ghost doubles, n_p cells, >= 4 ghost doubles; even pitch keeps every strip start
+        // (VRT_SLAB_GH + j0 - 3, j0 even) 16-byte aligned for the bulk-async (TMA) column loads
+        L.gx = 3; L.pitch = ((q0.n_p + VRT_SLAB_GH + 4 + 1) / 2) * 2;
+        L.plane = (long)(L.n_x + 2 * L.gx) * L.pitch + 1024;   // slack: the last strip's bulk load may run past the last column
         L.dx = c->F.dx; L.dp = sp.dp_finest;
         for (int k = 0; k < 3; k++) if ((rc = dev_alloc(c, S.allocations, &L.f[k], L.plane))) return rc;
         for (int k = 0; k < 5; k++) {
@@ -271,7 +273,7 @@ int vrt_patch_upload_f(vrt_ctx* c, int s, int patch, int state, const double* ho
         for (int cl = -L.gx; cl < L.n_x + L.gx; cl++) {
             int gi = L.x_begin + cl;
             if (gi < -2 || gi >= L.n_x_global + 2) continue;
-            VRT_CUDA(c, cudaMemcpyAsync(L.f[pi] + (long)(cl + L.gx) * L.pitch + 2, host + (long)(gi + 2) * hp, sizeof(double) * hp,
+            VRT_CUDA(c, cudaMemcpyAsync(L.f[pi] + (long)(cl + L.gx) * L.pitch + (VRT_SLAB_GH - 2), host + (long)(gi + 2) * hp, sizeof(double) * hp,
                                         cudaMemcpyHostToDevice, c->stream));
         }
         VRT_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -297,7 +299,7 @@ int vrt_patch_download_f(vrt_ctx* c, int s, int patch, int state, double* host) 
         // only this slab's own columns (plus the physical ghost columns it touches) are written to the host array
         int lo = L.left ? -2 : 0, hi = L.right ? L.n_x + 2 : L.n_x;
         VRT_CUDA(c, cudaMemcpy2DAsync(host + (long)(L.x_begin + lo + 2) * hp, sizeof(double) * hp,
-                                      L.f[pi] + (long)(lo + L.gx) * L.pitch + 2, sizeof(double) * L.pitch, sizeof(double) * hp, hi - lo,
+                                      L.f[pi] + (long)(lo + L.gx) * L.pitch + (VRT_SLAB_GH - 2), sizeof(double) * L.pitch, sizeof(double) * hp, hi - lo,
                                       cudaMemcpyDeviceToHost, c->stream));
         VRT_CUDA(c, cudaStreamSynchronize(c->stream));
         return 0;

@@ -39,7 +39,7 @@ __global__ void k_init_slab(VrtSlabDev L, double* plane, double pmin, int nvals,
     int cl = (int)(idx / L.n_p) - L.gx, j = (int)(idx % L.n_p);
     int gi = L.x_begin + cl;
     if (gi < 0 || gi >= L.n_x_global) return;   // physical ghost columns stay 0
-    plane[(long)(cl + L.gx) * L.pitch + 4 + j] = cell_average((double)gi, L.dx, pmin, L.dp, (double)j, nvals, xl, xr, n0, T);
+    plane[(long)(cl + L.gx) * L.pitch + VRT_SLAB_GH + j] = cell_average((double)gi, L.dx, pmin, L.dp, (double)j, nvals, xl, xr, n0, T);
 }
 }  // namespace
 

@@ -10,6 +10,7 @@
 #define VRT_MU_INV 795774.715482    // veritas.hpp:25
 #define VRT_CS 299792458.0          // veritas.hpp:26
 #define VRT_C_INV 3.33564095e-9     // veritas.hpp:27
+#define VRT_SLAB_GH 5               // ghost doubles below p-cell 0 in a slab column (odd: see vrt_set_hierarchy)
 
 // RK tableau, literal values of Rectangle.cpp:1397-1498 / EMSolver.cpp:210-312 (row s = stage s, row 5 = b)
 struct VrtTableau { double a[6][6]; };
