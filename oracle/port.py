@@ -56,6 +56,18 @@ def lib():
         L.vo_cfl_bound.argtypes = [C.POINTER(VoFields), C.c_int, dbl_p, dbl_p, dbl_p]
         L.vo_update_time.restype = C.c_double
         L.vo_update_time.argtypes = [C.c_double, C.c_int, C.c_double]
+        pp = C.POINTER(C.POINTER(VoPatch))
+        L.vo_mesh_create.restype = C.c_void_p
+        L.vo_mesh_create.argtypes = [C.c_int, C.c_int, C.c_int, pp, C.POINTER(C.c_int)]
+        L.vo_mesh_destroy.argtypes = [C.c_void_p]
+        L.vo_mesh_get_strips.restype = C.c_int
+        L.vo_mesh_get_strips.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_ubyte)]
+        L.vo_mesh_get_flags.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_ubyte)]
+        L.vo_mesh_push_data.argtypes = [C.c_void_p, C.c_int]
+        L.vo_mesh_push_boundary_c.argtypes = [C.c_void_p]
+        L.vo_mesh_substep.argtypes = [C.c_void_p, C.POINTER(VoFields), C.c_int, C.c_double, C.c_int, C.c_int]
+        L.vo_mesh_advance.argtypes = [C.c_void_p, C.POINTER(VoFields), C.c_double, C.c_int]
+        L.vo_mesh_moments.argtypes = [C.c_void_p, C.POINTER(VoFields), dbl_p, dbl_p, dbl_p]
         _LIB = L
     return _LIB
 
@@ -216,3 +228,131 @@ class SingleLevelOracle:
             if base + "FxL" in dump:
                 P.FxL[:] = dump[base + "FxL"][:, :, 0]
                 P.FpL[:] = dump[base + "FpL"][:, :, 0]
+
+
+def hierarchy_from_dump(dump, tag, n_species=2):
+    """Patch descriptors per species from a ref_harness record group, in the reference's order: levels[0] (finest,
+    depth 0) first, Level::rectangles order inside a level (Mesh.cpp:814)."""
+    out = []
+    for s in range(n_species):
+        descs, l = [], 0
+        while f"{tag}/s{s}/l{l}/r0/desc" in dump or any(k.startswith(f"{tag}/s{s}/l{l + 1}/") for k in dump):
+            r = 0
+            while f"{tag}/s{s}/l{l}/r{r}/desc" in dump:
+                d = dump[f"{tag}/s{s}/l{l}/r{r}/desc"]
+                descs.append(dict(depth=int(d[4]), x_pos=int(d[2]), p_pos=int(d[3]), n_x=int(d[0]), n_p=int(d[1]),
+                                  up=int(d[5]), down=int(d[6]), left=int(d[7]), right=int(d[8]), key=f"s{s}/l{l}/r{r}"))
+                r += 1
+            l += 1
+        out.append(descs)
+    return out
+
+
+class MeshOracle:
+    """SolverManager over multi-level meshes (one vo_mesh per species): restates SolverManager::Advance
+    (SolverManager.cpp:28-39) with Mesh::Advance / PushData / PushBoundaryC and the moment assembly on the C port."""
+
+    def __init__(self, x_size_finest, dx_finest, species, hierarchies, r=2, max_depth=None, laser=None, poisson=True):
+        self.L = lib()
+        self.species = species
+        self.r = r
+        self.N = x_size_finest
+        self.max_depth = max(d["depth"] for h in hierarchies for d in h) if max_depth is None else max_depth
+        self.fields = Fields(x_size_finest, dx_finest)
+        self.time = 0.0
+        self.laser = laser or (lambda t: (0.0, 0.0))
+        self.charges = [np.zeros(self.N) for _ in species]
+        self._scratch = np.zeros(4 * self.N)
+        self.poisson = self.L.vo_poisson_create(self.N) if poisson else None
+        self.meshes, self.patches, self.descs = [], [], hierarchies
+        for sp, h in zip(species, hierarchies):
+            ps = []
+            for d in h:
+                sc = float(r) ** d["depth"]
+                ps.append(Patch(d["n_x"], d["n_p"], sc * dx_finest, sc * sp["dp"], sp["pmin"], sp["m"], sp["q"], x_pos=d["x_pos"],
+                                p_pos=d["p_pos"], up=d["up"], down=d["down"], left=d["left"], right=d["right"], rtb=int(r ** d["depth"])))
+            arr = (C.POINTER(VoPatch) * len(ps))(*[C.pointer(p.c) for p in ps])
+            depth = (C.c_int * len(ps))(*[d["depth"] for d in h])
+            self.meshes.append(self.L.vo_mesh_create(len(ps), r, self.max_depth + 1, arr, depth))
+            self.patches.append(ps)
+
+    def __del__(self):
+        for m in getattr(self, "meshes", []):
+            self.L.vo_mesh_destroy(m)
+        self.meshes = []
+        if getattr(self, "poisson", None):
+            self.L.vo_poisson_destroy(self.poisson)
+            self.poisson = None
+
+    def strips(self, s, p, side):
+        P = self.patches[s][p]
+        n = (P.n_p // self.r + 2) if side < 2 else P.n_x // self.r
+        nb = (C.c_int * n)(); same = (C.c_ubyte * n)()
+        self.L.vo_mesh_get_strips(self.meshes[s], p, side, nb, same)
+        return list(nb), list(same)
+
+    def flags(self, s, p):
+        P = self.patches[s][p]
+        out = np.zeros((P.n_x + 4, P.n_p + 4), dtype=np.uint8)
+        self.L.vo_mesh_get_flags(self.meshes[s], p, out.ctypes.data_as(C.POINTER(C.c_ubyte)))
+        return out
+
+    def assemble(self):
+        F = self.fields
+        F.charge[:] = 0.0
+        F.J[:] = 0.0
+        for s, m in enumerate(self.meshes):
+            self.charges[s][:] = 0.0
+            self.L.vo_mesh_moments(m, C.byref(F.c), _p(self.charges[s]), _p(F.J), _p(self._scratch))
+        for s in range(len(self.meshes)):
+            F.charge[:] = F.charge + self.charges[s]
+
+    def update_potential(self, phi_inject=None):
+        F = self.fields
+        if phi_inject is not None:
+            F.PHI[:] = phi_inject
+            self.L.vo_update_ex0(C.byref(F.c))
+        else:
+            self.L.vo_update_potential(self.poisson, C.byref(F.c))
+
+    def stage(self, dt, i, phi_inject=None):
+        self.assemble()
+        self.update_potential(phi_inject)
+        for m in self.meshes:
+            self.L.vo_mesh_advance(m, C.byref(self.fields.c), dt, i)
+        self.time = self.L.vo_update_time(self.time, i, dt)
+        by0, bz0 = self.laser(self.time)
+        self.L.vo_field_stage(C.byref(self.fields.c), i, dt, by0, bz0)
+
+    def advance(self, dt, phi_inject=None):
+        for i in range(6):
+            self.stage(dt, i, None if phi_inject is None else phi_inject[i])
+
+    def push_data(self, s, val):
+        self.L.vo_mesh_push_data(self.meshes[s], val)
+
+    def push_boundary_c(self, s):
+        self.L.vo_mesh_push_boundary_c(self.meshes[s])
+
+    def substep(self, s, depth, dt, step, sub):
+        self.L.vo_mesh_substep(self.meshes[s], C.byref(self.fields.c), depth, dt, step, sub)
+
+    def load_reference_state(self, dump, tag):
+        F = self.fields
+        for k in ("By", "Bz", "Ey", "Ez", "Ay", "Az"):
+            F.a[k][:] = dump[f"{tag}/{k}"]
+        F.a_squared[:] = dump[f"{tag}/a_squared"]
+        F.PHI[:] = dump[f"{tag}/PHI"]
+        F.charge[:] = dump[f"{tag}/charge"]
+        F.J[:] = dump[f"{tag}/J"]
+        F.neutral[:] = dump[f"{tag}/neutralizationCharge"]
+        F.Ex0 = float(dump[f"{tag}/Ex0"][0])
+        self.time = float(dump[f"{tag}/time"][0])
+        for s, h in enumerate(self.descs):
+            for P, d in zip(self.patches[s], h):
+                base = f"{tag}/{d['key']}/"
+                if base + "f" in dump:
+                    f = dump[base + "f"]
+                    P.f0[:] = f[:, :, 0]; P.f1[:] = f[:, :, 1]; P.f2[:] = f[:, :, 2]
+                else:
+                    P.f0[:] = dump[base + "f0"]; P.f1[:] = dump[base + "f1"]

@@ -110,8 +110,11 @@ static const double RK_A[6][6] = {
     {0.2014243506726763, 0.008742057842904185, 0.15993995707168115, 0.4038290605220775, 0.22606457389066084, 0},
     {0.15791629516167136, 0.0, 0.18675894052400077, 0.6805652953093346, -0.27524053099500667, 0.25}};
 
-/* Rectangle::FCTTimeStep (Rectangle.cpp:1255-1623) for a patch without interior level boundaries. */
-void vo_fct_substep(vo_patch* P, const vo_fields* F, double timestep, int step, int subStep) {
+/* Rectangle::FCTTimeStep (Rectangle.cpp:1255-1623).  M/pidx (may be NULL/-1) give the mesh the patch belongs to: faces
+ * flagged is_interrior_level_boundary_{x,p} then take their fluxes from the finer patch (defined in the AMR part below). */
+struct vo_mesh_s;
+static void replace_level_boundary_fluxes_hook(void* M, const vo_fields* F, int p, int step);
+static void fct_substep_impl(vo_patch* P, const vo_fields* F, double timestep, int step, int subStep, void* M, int pidx) {
     const int nx = P->n_x, np = P->n_p;
     const int xm = P->left ? 1 : 0, xp = P->right ? nx : nx + 1;
     const int pp = P->up ? np : np + 1, pm = P->down ? 1 : 0;
@@ -166,6 +169,7 @@ void vo_fct_substep(vo_patch* P, const vo_fields* F, double timestep, int step, 
                 if (step == 0) P->FpL[c] = dp_inv * ((am > 0.0 ? P->f1[c - 1] : P->f1[c]) * am);
             }
         }
+        if (M) replace_level_boundary_fluxes_hook(M, F, pidx, step);
         /* RK combination over the whole padded array (Rectangle.cpp:1396-1517) */
         double a[6], aSum = 0.0;
         for (int k = 0; k <= step; k++) { a[k] = RK_A[step][k] * timestep; aSum = (k == 0) ? a[0] : aSum + a[k]; }
@@ -228,6 +232,10 @@ void vo_fct_substep(vo_patch* P, const vo_fields* F, double timestep, int step, 
     } else if (subStep == 3) {
         memcpy(P->f0, P->f1, sizeof(double) * npad);
     }
+}
+
+void vo_fct_substep(vo_patch* P, const vo_fields* F, double timestep, int step, int subStep) {
+    fct_substep_impl(P, F, timestep, step, subStep, NULL, -1);
 }
 
 /* Ghost fill of state `val` (1 or 2) for a patch whose every neighbour is the physical boundary:
@@ -302,7 +310,7 @@ void vo_patch_moments(const vo_patch* P, const vo_fields* F, const unsigned char
             for (int k = 0; k < rtb; k++) t[k] += cor;
         }
         for (int j = 0; j < np; j++) {
-            if (!(nested && nested[NS(P, i, j)])) {
+            if (!(nested && (nested[NS(P, i, j)] & 1))) {
                 for (int k = 0; k < rtb; k++) {
                     double a2 = cell_a_sq(F, (i + P->x_pos) * rtb + k);
                     chargeR[i * rtb + k] += t0[k];
@@ -504,4 +512,489 @@ void vo_assemble_single(int n_species, vo_patch** P, vo_fields* F, double** char
         }
     }
     for (int s = 0; s < n_species; s++) for (int i = 0; i < N; i++) F->charge[i] += charges[s][i];
+}
+
+/* =====================================================================================================
+ * AMR: multi-patch, multi-level meshes.  One vo_mesh = one Mesh (one species).
+ * Levels are indexed by depth, 0 = finest (Mesh.cpp:814).  Patch order inside a level is the caller's order =
+ * the reference's Level::rectangles order; the connectivity tables depend on it (later calls overwrite).
+ * ===================================================================================================== */
+enum { VO_NESTED = 1, VO_LBX = 2, VO_LBP = 4 };
+typedef struct {
+    int depth, ns_x, ns_p;        /* strips per x side (n_p/r + 2) and per p side (n_x/r)  (Rectangle.cpp:40-48) */
+    int* nb[4];                   /* 0 xm, 1 xp, 2 pm, 3 pp: neighbour patch index, -1 = the BoundaryCondition object */
+    unsigned char* same[4];       /* is_exterrior_boundary_same_level_* */
+    int *finer, *finer_x, *finer_p;   /* per padded cell: patch index or -1 (finer_level, finer_level_x, finer_level_p) */
+    unsigned char* flags;         /* VO_NESTED | VO_LBX | VO_LBP per padded cell */
+} vo_conn;
+typedef struct {
+    int n, r, n_levels;
+    vo_patch** P;
+    vo_conn* C;
+    int* level_start;             /* n_levels + 1 offsets into order[] */
+    int* order;                   /* patch indices grouped by depth, caller order inside a level */
+    double coefs_ref[3 * 8];      /* interpolatCoefsREF (Rectangle.cpp:94-101) */
+} vo_mesh;
+
+static int on_line(int x, int y1, int y2) { return ((x - y1) > -1) && ((y2 - x) > -1); }   /* Rectangle.cpp:667-669 */
+static int imax(int a, int b) { return a > b ? a : b; }
+static int imin(int a, int b) { return a < b ? a : b; }
+
+/* Rectangle::CalculateConnectivityFromFiner (Rectangle.cpp:768-864): ic = current (coarse), jf = rectangle (finer) */
+static void conn_from_finer(vo_mesh* M, int ic, int jf) {
+    const int r = M->r;
+    vo_patch *Cc = M->P[ic], *Ff = M->P[jf];
+    vo_conn *cc = &M->C[ic], *cf = &M->C[jf];
+    const int n_x = Cc->n_x, n_p = Cc->n_p;
+    int x_pos_2 = Ff->x_pos / r - Cc->x_pos, p_pos_2 = Ff->p_pos / r - Cc->p_pos;
+    int n_x_2 = Ff->n_x / r, n_p_2 = Ff->n_p / r;
+    int lower_x = imax(0, x_pos_2), upper_x = imin(n_x, x_pos_2 + n_x_2);
+    int lower_p = imax(0, p_pos_2), upper_p = imin(n_p, p_pos_2 + n_p_2);
+    for (int i = lower_x; i < upper_x; i++)
+        for (int j = lower_p; j < upper_p; j++) { cc->flags[NS(Cc, i, j)] |= VO_NESTED; cc->finer[NS(Cc, i, j)] = jf; }
+    if (((x_pos_2 + n_x_2) < (n_x + 1)) && ((x_pos_2 + n_x_2) > -1))
+        for (int i = lower_p; i < upper_p; i++) { cc->finer_x[NS(Cc, x_pos_2 + n_x_2, i)] = jf; cc->flags[NS(Cc, x_pos_2 + n_x_2, i)] |= VO_LBX; }
+    if (((x_pos_2 + n_x_2) < n_x) && ((x_pos_2 + n_x_2) > -1)) {
+        for (int i = lower_p; i < upper_p; i++) { int j = i - p_pos_2 + 1; cf->nb[1][j] = ic; cf->same[1][j] = 0; }
+        if (on_line(p_pos_2 - 1, 0, n_p - 1)) { cf->nb[1][0] = ic; cf->same[1][0] = 0; }
+        if (on_line(p_pos_2 + n_p_2, 0, n_p - 1)) { cf->nb[1][cf->ns_x - 1] = ic; cf->same[1][cf->ns_x - 1] = 0; }
+    }
+    if ((x_pos_2 < (n_x + 1)) && (x_pos_2 > -1))
+        for (int i = lower_p; i < upper_p; i++) { cc->finer_x[NS(Cc, x_pos_2, i)] = jf; cc->flags[NS(Cc, x_pos_2, i)] |= VO_LBX; }
+    if ((x_pos_2 < (n_x + 1)) && (x_pos_2 > 0)) {
+        for (int i = lower_p; i < upper_p; i++) { int j = i - p_pos_2 + 1; cf->nb[0][j] = ic; cf->same[0][j] = 0; }
+        if (on_line(p_pos_2 - 1, 0, n_p - 1)) { cf->nb[0][0] = ic; cf->same[0][0] = 0; }
+        if (on_line(p_pos_2 + n_p_2, 0, n_p - 1)) { cf->nb[0][cf->ns_x - 1] = ic; cf->same[0][cf->ns_x - 1] = 0; }
+    }
+    if (((p_pos_2 + n_p_2) < (n_p + 1)) && ((p_pos_2 + n_p_2) > -1))
+        for (int i = lower_x; i < upper_x; i++) { cc->finer_p[NS(Cc, i, p_pos_2 + n_p_2)] = jf; cc->flags[NS(Cc, i, p_pos_2 + n_p_2)] |= VO_LBP; }
+    if (((p_pos_2 + n_p_2) < n_p) && ((p_pos_2 + n_p_2) > -1))
+        for (int i = lower_x; i < upper_x; i++) { int j = i - x_pos_2; cf->nb[3][j] = ic; cf->same[3][j] = 0; }
+    if ((p_pos_2 < (n_p + 1)) && (p_pos_2 > -1))
+        for (int i = lower_x; i < upper_x; i++) { cc->finer_p[NS(Cc, i, p_pos_2)] = jf; cc->flags[NS(Cc, i, p_pos_2)] |= VO_LBP; }
+    if ((p_pos_2 < (n_p + 1)) && (p_pos_2 > 0))
+        for (int i = lower_x; i < upper_x; i++) { int j = i - x_pos_2; cf->nb[2][j] = ic; cf->same[2][j] = 0; }
+}
+
+/* Rectangle::CalculateConnectivitySame (Rectangle.cpp:671-766): a = this, b = rectangle */
+static void conn_same(vo_mesh* M, int a, int b) {
+    const int r = M->r;
+    vo_patch *A = M->P[a], *B = M->P[b];
+    vo_conn* ca = &M->C[a];
+    const int n_x = A->n_x, n_p = A->n_p, x_pos = A->x_pos, p_pos = A->p_pos;
+    const int n_x_2 = B->n_x, n_p_2 = B->n_p, x_pos_2 = B->x_pos, p_pos_2 = B->p_pos;
+    const int x_pos_r = x_pos_2 - x_pos, p_pos_r = p_pos_2 - p_pos;
+    const int last = ca->ns_x - 1;
+    if (x_pos_r == n_x) {
+        int lower = imax(p_pos_2, p_pos), upper = imin(p_pos + n_p, p_pos_2 + n_p_2);
+        if (on_line(-1, p_pos_r, p_pos_r + n_p_2 - 1)) { ca->nb[1][0] = b; ca->same[1][0] = 1; }
+        if (on_line(n_p, p_pos_r, p_pos_r + n_p_2 - 1)) { ca->nb[1][last] = b; ca->same[1][last] = 1; }
+        while (lower < upper) { int i1 = (lower - p_pos) / r + 1; ca->nb[1][i1] = b; ca->same[1][i1] = 1; lower += r; }
+    }
+    if (x_pos_r == -n_x_2) {
+        int lower = imax(p_pos_2, p_pos), upper = imin(p_pos + n_p, p_pos_2 + n_p_2);
+        if (on_line(-1, p_pos_r, p_pos_r + n_p_2 - 1)) { ca->nb[0][0] = b; ca->same[0][0] = 1; }
+        if (on_line(n_p, p_pos_r, p_pos_r + n_p_2 - 1)) { ca->nb[0][last] = b; ca->same[0][last] = 1; }
+        while (lower < upper) { int i1 = (lower - p_pos) / r + 1; ca->nb[0][i1] = b; ca->same[0][i1] = 1; lower += r; }
+    }
+    if (p_pos_r == n_p) {
+        int lower = imax(x_pos_2, x_pos), upper = imin(x_pos + n_x, x_pos_2 + n_x_2);
+        if (on_line(-1, x_pos_r, x_pos_r + n_x_2 - 1)) { ca->nb[0][last] = b; ca->same[0][last] = 1; }
+        if (on_line(n_x, x_pos_r, x_pos_r + n_x_2 - 1)) { ca->nb[1][last] = b; ca->same[1][last] = 1; }
+        while (lower < upper) { int i1 = (lower - x_pos) / r; ca->nb[3][i1] = b; ca->same[3][i1] = 1; lower += r; }
+    }
+    if (p_pos_r == -n_p_2) {
+        int lower = imax(x_pos_2, x_pos), upper = imin(x_pos + n_x, x_pos_2 + n_x_2);
+        if (on_line(-1, x_pos_r, x_pos_r + n_x_2 - 1)) { ca->nb[0][0] = b; ca->same[0][0] = 1; }
+        if (on_line(n_x, x_pos_r, x_pos_r + n_x_2 - 1)) { ca->nb[1][0] = b; ca->same[1][0] = 1; }
+        while (lower < upper) { int i1 = (lower - x_pos) / r; ca->nb[2][i1] = b; ca->same[2][i1] = 1; lower += r; }
+    }
+}
+
+/* Rectangle ctor tables + the connectivity passes of Mesh::promoteHierarchyToMesh (Mesh.cpp:840-861) */
+vo_mesh* vo_mesh_create(int n, int r, int n_levels, vo_patch** patches, const int* depth) {
+    vo_mesh* M = (vo_mesh*)calloc(1, sizeof(vo_mesh));
+    M->n = n; M->r = r; M->n_levels = n_levels;
+    M->P = (vo_patch**)malloc(sizeof(vo_patch*) * n);
+    M->C = (vo_conn*)calloc(n, sizeof(vo_conn));
+    M->order = (int*)malloc(sizeof(int) * n);
+    M->level_start = (int*)calloc(n_levels + 1, sizeof(int));
+    interp_coefs(r, M->coefs_ref);
+    int k = 0;
+    for (int l = 0; l < n_levels; l++) {
+        M->level_start[l] = k;
+        for (int p = 0; p < n; p++) if (depth[p] == l) M->order[k++] = p;
+    }
+    M->level_start[n_levels] = k;
+    for (int p = 0; p < n; p++) {
+        vo_patch* P = patches[p]; vo_conn* c = &M->C[p];
+        M->P[p] = P; c->depth = depth[p];
+        c->ns_x = P->n_p / r + 2; c->ns_p = P->n_x / r;
+        long npad = (long)(P->n_x + 4) * (P->n_p + 4);
+        for (int s = 0; s < 4; s++) {
+            int ns = s < 2 ? c->ns_x : c->ns_p;
+            c->nb[s] = (int*)malloc(sizeof(int) * ns); c->same[s] = (unsigned char*)malloc(ns);
+            for (int i = 0; i < ns; i++) { c->nb[s][i] = -1; c->same[s][i] = 1; }
+        }
+        c->finer = (int*)malloc(sizeof(int) * npad); c->finer_x = (int*)malloc(sizeof(int) * npad); c->finer_p = (int*)malloc(sizeof(int) * npad);
+        for (long i = 0; i < npad; i++) { c->finer[i] = -1; c->finer_x[i] = -1; c->finer_p[i] = -1; }
+        c->flags = (unsigned char*)calloc(npad, 1);
+    }
+    for (int l = 1; l < n_levels; l++)
+        for (int a = M->level_start[l]; a < M->level_start[l + 1]; a++)
+            for (int b = M->level_start[l - 1]; b < M->level_start[l]; b++) conn_from_finer(M, M->order[a], M->order[b]);
+    for (int l = 0; l < n_levels; l++)
+        for (int a = M->level_start[l]; a < M->level_start[l + 1]; a++)
+            for (int b = M->level_start[l]; b < M->level_start[l + 1]; b++) if (a != b) conn_same(M, M->order[a], M->order[b]);
+    return M;
+}
+void vo_mesh_destroy(vo_mesh* M) {
+    for (int p = 0; p < M->n; p++) {
+        vo_conn* c = &M->C[p];
+        for (int s = 0; s < 4; s++) { free(c->nb[s]); free(c->same[s]); }
+        free(c->finer); free(c->finer_x); free(c->finer_p); free(c->flags);
+    }
+    free(M->P); free(M->C); free(M->order); free(M->level_start); free(M);
+}
+/* test access to the derived tables: side 0..3 -> nb/same strips; returns the strip count */
+int vo_mesh_get_strips(const vo_mesh* M, int p, int side, int* nb, unsigned char* same) {
+    const vo_conn* c = &M->C[p]; int ns = side < 2 ? c->ns_x : c->ns_p;
+    for (int i = 0; i < ns; i++) { nb[i] = c->nb[side][i]; same[i] = c->same[side][i]; }
+    return ns;
+}
+void vo_mesh_get_flags(const vo_mesh* M, int p, unsigned char* flags) {
+    const vo_patch* P = M->P[p]; memcpy(flags, M->C[p].flags, (size_t)(P->n_x + 4) * (P->n_p + 4));
+}
+
+static inline double* fstate(vo_patch* P, int val) { return val == 2 ? P->f2 : (val == 1 ? P->f1 : P->f0); }
+/* Rectangle::GetValueFromSameLevel (Rectangle.cpp:307-312); nb < 0 = BoundaryCondition (BoundaryCondition.cpp:6-8) */
+static double same_level_value(vo_mesh* M, int nb, int i, int j, int val) {
+    if (nb < 0) return 0.0;
+    vo_patch* Q = M->P[nb];
+    return fstate(Q, val)[NS(Q, i - Q->x_pos, j - Q->p_pos)];
+}
+/* Rectangle::GetValueFromFinerLevel (Rectangle.cpp:314-327) on the finer patch nb */
+static double finer_level_value(vo_mesh* M, int nb, int i, int j, int val) {
+    vo_patch* Q = M->P[nb]; const int r = M->r;
+    int i_f = i * r - Q->x_pos, j_f = j * r - Q->p_pos;
+    double t = 0.0;
+    for (int k = 0; k < r; k++) for (int l = 0; l < r; l++) t += fstate(Q, val)[NS(Q, i_f + k, j_f + l)];
+    t /= pow((double)r, 2.0);
+    return t;
+}
+/* Rectangle::GetWenoValueFromCoarseLevel (Rectangle.cpp:343-415) on the coarse patch nb; out has r*r (d = -1) or 2r values */
+static void coarse_level_values(vo_mesh* M, int nb, int i, int j, int d, int val, double* out) {
+    vo_patch* Q = M->P[nb]; const int r = M->r;
+    const double* f = fstate(Q, val);
+    int ic = i / r - Q->x_pos, jc = j / r - Q->p_pos;
+    double temps[5][8], ip[64], part[8], sum = 0.0;
+    for (int k = -2; k < 3; k++)
+        interpolants(M->coefs_ref, r, f[NS(Q, ic - 2, jc + k)], f[NS(Q, ic - 1, jc + k)], f[NS(Q, ic, jc + k)], f[NS(Q, ic + 1, jc + k)], f[NS(Q, ic + 2, jc + k)], temps[k + 2]);
+    for (int k = 0; k < r; k++) {
+        interpolants(M->coefs_ref, r, temps[0][k], temps[1][k], temps[2][k], temps[3][k], temps[4][k], part);
+        for (int l = 0; l < r; l++) { ip[k * r + l] = part[l]; sum += part[l]; }
+    }
+    double correction = f[NS(Q, ic, jc)] - 1.0 / pow((double)r, 2) * sum;
+    for (int k = 0; k < r * r; k++) ip[k] += correction;
+    if (d == 0) for (int k = 0; k < r; k++) { out[2 * k] = ip[r * k + r - 1]; out[2 * k + 1] = ip[r * k + r - 2]; }
+    else if (d == 1) for (int k = 0; k < r; k++) { out[2 * k] = ip[k]; out[2 * k + 1] = ip[r + k]; }
+    else if (d == 2) for (int k = 0; k < r; k++) { out[2 * k] = ip[r * k]; out[2 * k + 1] = ip[r * k + 1]; }
+    else if (d == 3) for (int k = 0; k < r; k++) { out[2 * k] = ip[r * (r - 1) + k]; out[2 * k + 1] = ip[r * (r - 2) + k]; }
+    else for (int k = 0; k < r * r; k++) out[k] = ip[k];
+}
+/* Rectangle::UpdateInterriorPoints (Rectangle.cpp:329-337) */
+static void update_interior_points(vo_mesh* M, int p, int val) {
+    vo_patch* P = M->P[p]; vo_conn* c = &M->C[p]; double* f = fstate(P, val);
+    for (int i = 0; i < P->n_x; i++)
+        for (int j = 0; j < P->n_p; j++)
+            if (c->flags[NS(P, i, j)] & VO_NESTED) f[NS(P, i, j)] = finer_level_value(M, c->finer[NS(P, i, j)], P->x_pos + i, P->p_pos + j, val);
+}
+/* Rectangle::UpdateSameLevelBoundaries (Rectangle.cpp:562-614) */
+static void update_same_level_boundaries(vo_mesh* M, int p, int val) {
+    vo_patch* P = M->P[p]; vo_conn* c = &M->C[p]; double* f = fstate(P, val); const int r = M->r;
+    const int n_x = P->n_x, n_p = P->n_p, x_pos = P->x_pos, p_pos = P->p_pos;
+    for (int i = 0; i < c->ns_x - 2; i++) if (c->same[0][i + 1]) for (int j = 0; j < r; j++) {
+        f[NS(P, -1, i * r + j)] = same_level_value(M, c->nb[0][i + 1], x_pos - 1, p_pos + i * r + j, val);
+        f[NS(P, -2, i * r + j)] = same_level_value(M, c->nb[0][i + 1], x_pos - 2, p_pos + i * r + j, val);
+    }
+    for (int i = 0; i < c->ns_x - 2; i++) if (c->same[1][i + 1]) for (int j = 0; j < r; j++) {
+        f[NS(P, n_x, i * r + j)] = same_level_value(M, c->nb[1][i + 1], x_pos + n_x, p_pos + i * r + j, val);
+        f[NS(P, n_x + 1, i * r + j)] = same_level_value(M, c->nb[1][i + 1], x_pos + n_x + 1, p_pos + i * r + j, val);
+    }
+    for (int i = 0; i < c->ns_p; i++) if (c->same[2][i]) for (int j = 0; j < r; j++) {
+        f[NS(P, i * r + j, -1)] = same_level_value(M, c->nb[2][i], x_pos + i * r + j, p_pos - 1, val);
+        f[NS(P, i * r + j, -2)] = same_level_value(M, c->nb[2][i], x_pos + i * r + j, p_pos - 2, val);
+    }
+    for (int i = 0; i < c->ns_p; i++) if (c->same[3][i]) for (int j = 0; j < r; j++) {
+        f[NS(P, i * r + j, n_p)] = same_level_value(M, c->nb[3][i], x_pos + i * r + j, p_pos + n_p, val);
+        f[NS(P, i * r + j, n_p + 1)] = same_level_value(M, c->nb[3][i], x_pos + i * r + j, p_pos + n_p + 1, val);
+    }
+}
+/* Rectangle::UpdateCornerPoints (Rectangle.cpp:1130-1214) = the corner blocks of UpdateDifferentLevelBoundaries (484-560) */
+static void update_corner_points(vo_mesh* M, int p, int val) {
+    vo_patch* P = M->P[p]; vo_conn* c = &M->C[p]; double* f = fstate(P, val); const int r = M->r;
+    const int n_x = P->n_x, x_pos = P->x_pos, p_pos = P->p_pos;
+    double temp[16];
+    for (int side = 0; side < 2; side++) {            /* 0: xm (ghost columns -1,-2), 1: xp (n_x, n_x+1) */
+        const int g1 = side == 0 ? -1 : n_x, g2 = side == 0 ? -2 : n_x + 1;
+        const int q1 = side == 0 ? x_pos - 1 : x_pos + n_x, q2 = side == 0 ? x_pos - 2 : x_pos + n_x + 1;
+        const int d = side == 0 ? 3 : 1;
+        for (int which = 0; which < 2; which++) {     /* 0: lower corner (strip -1), 1: upper corner */
+            const int i = which == 0 ? -1 : c->ns_x - 2;
+            const int j0 = which == 0 ? r - 2 : 0, j1 = which == 0 ? r : 2;
+            const int e = i + 1;
+            if (!c->same[side][e]) {
+                coarse_level_values(M, c->nb[side][e], q1, p_pos + i * r, d, val, temp);
+                for (int j = j0; j < j1; j++) { f[NS(P, g1, i * r + j)] = temp[2 * j]; f[NS(P, g2, i * r + j)] = temp[2 * j + 1]; }
+            } else {
+                for (int j = j0; j < j1; j++) {
+                    f[NS(P, g1, i * r + j)] = same_level_value(M, c->nb[side][e], q1, p_pos + i * r + j, val);
+                    f[NS(P, g2, i * r + j)] = same_level_value(M, c->nb[side][e], q2, p_pos + i * r + j, val);
+                }
+            }
+        }
+    }
+}
+/* Rectangle::UpdateDifferentLevelBoundaries (Rectangle.cpp:417-560) */
+static void update_different_level_boundaries(vo_mesh* M, int p, int val) {
+    vo_patch* P = M->P[p]; vo_conn* c = &M->C[p]; double* f = fstate(P, val); const int r = M->r;
+    const int n_x = P->n_x, n_p = P->n_p, x_pos = P->x_pos, p_pos = P->p_pos;
+    double temp[16];
+    for (int i = 0; i < c->ns_x - 2; i++) if (!c->same[0][i + 1]) {
+        coarse_level_values(M, c->nb[0][i + 1], x_pos - 1, p_pos + i * r, 3, val, temp);
+        for (int j = 0; j < r; j++) { f[NS(P, -1, i * r + j)] = temp[2 * j]; f[NS(P, -2, i * r + j)] = temp[2 * j + 1]; }
+    }
+    for (int i = 0; i < c->ns_x - 2; i++) if (!c->same[1][i + 1]) {
+        coarse_level_values(M, c->nb[1][i + 1], x_pos + n_x, p_pos + i * r, 1, val, temp);
+        for (int j = 0; j < r; j++) { f[NS(P, n_x, i * r + j)] = temp[2 * j]; f[NS(P, n_x + 1, i * r + j)] = temp[2 * j + 1]; }
+    }
+    for (int i = 0; i < c->ns_p; i++) if (!c->same[2][i]) {
+        coarse_level_values(M, c->nb[2][i], x_pos + i * r, p_pos - 1, 0, val, temp);
+        for (int j = 0; j < r; j++) { f[NS(P, i * r + j, -1)] = temp[2 * j]; f[NS(P, i * r + j, -2)] = temp[2 * j + 1]; }
+    }
+    for (int i = 0; i < c->ns_p; i++) if (!c->same[3][i]) {
+        coarse_level_values(M, c->nb[3][i], x_pos + i * r, p_pos + n_p, 2, val, temp);
+        for (int j = 0; j < r; j++) { f[NS(P, i * r + j, n_p)] = temp[2 * j]; f[NS(P, i * r + j, n_p + 1)] = temp[2 * j + 1]; }
+    }
+    update_corner_points(M, p, val);
+}
+/* Level::PushData (Level.cpp:88-126), update types 0..3 */
+static void level_push(vo_mesh* M, int l, int type, int val) {
+    for (int a = M->level_start[l]; a < M->level_start[l + 1]; a++) {
+        int p = M->order[a];
+        if (type == 0) update_interior_points(M, p, val);
+        else if (type == 1) update_same_level_boundaries(M, p, val);
+        else if (type == 2) update_different_level_boundaries(M, p, val);
+        else update_corner_points(M, p, val);
+    }
+}
+/* Mesh::PushData (Mesh.cpp:91-106) */
+void vo_mesh_push_data(vo_mesh* M, int val) {
+    const int nl = M->n_levels;
+    level_push(M, 0, 1, val);
+    for (int i = 1; i < nl; i++) { level_push(M, i, 0, val); level_push(M, i, 1, val); }
+    level_push(M, nl - 1, 3, val);
+    for (int i = nl - 1; i > 0; i--) level_push(M, i - 1, 2, val);
+}
+
+/* ---- coarse-fine flux matching: RGKGetFlux{X,P,XL,PL} + CalculateFluxToCoarse* (Rectangle.cpp:1032-1098, 1216-1253;
+ * Rectangle.hpp:132-178).  Recursive through the levels, recomputed from the finer patch's f1. */
+static double rgk_flux(vo_mesh* M, const vo_fields* F, int p, int i, int j, int kind);   /* kind 0 X, 1 P, 2 XL, 3 PL */
+static double flux_to_coarse(vo_mesh* M, const vo_fields* F, int p, int i, int j, int kind) {
+    vo_patch* P = M->P[p]; const int r = M->r;
+    i = i * r - P->x_pos; j = j * r - P->p_pos;
+    double t = 0.0;
+    for (int k = 0; k < r; k++) t += (kind == 0 || kind == 2) ? rgk_flux(M, F, p, i, j + k, kind) : rgk_flux(M, F, p, i + k, j, kind);
+    t *= (1.0 / (r * r));
+    return t;
+}
+static double rgk_flux(vo_mesh* M, const vo_fields* F, int p, int i, int j, int kind) {
+    vo_patch* P = M->P[p]; vo_conn* c = &M->C[p];
+    const long idx = NS(P, i, j);
+    const int isx = (kind == 0 || kind == 2);
+    if (c->flags[idx] & (isx ? VO_LBX : VO_LBP))
+        return flux_to_coarse(M, F, isx ? c->finer_x[idx] : c->finer_p[idx], P->x_pos + i, P->p_pos + j, kind);
+    const double w3 = 1.0 / 48.0, dx_inv = 1 / P->dx, dp_inv = 1 / P->dp, q = P->q, cc = CS * CS * P->m;
+    const double* f = P->f1;
+    if (kind == 0) {
+        double as = q * q * a_sq(F, finest_index(P, i));
+        double am = dp_inv * cc * (gamma_(P, momentum(P, j + 1), as) - gamma_(P, momentum(P, j), as));
+        double ap1 = dp_inv * cc * (gamma_(P, momentum(P, j + 2.0), as) - gamma_(P, momentum(P, j + 1.0), as));
+        double am1 = dp_inv * cc * (gamma_(P, momentum(P, j), as) - gamma_(P, momentum(P, j - 1.0), as));
+        double fm = vo_weno(f[NS(P, i - 2, j)], f[NS(P, i - 1, j)], f[NS(P, i, j)], f[NS(P, i + 1, j)], am > 0.0);
+        double fp1 = vo_weno(f[NS(P, i - 2, j + 1)], f[NS(P, i - 1, j + 1)], f[NS(P, i, j + 1)], f[NS(P, i + 1, j + 1)], ap1 > 0.0);
+        double fm1 = vo_weno(f[NS(P, i - 2, j - 1)], f[NS(P, i - 1, j - 1)], f[NS(P, i, j - 1)], f[NS(P, i + 1, j - 1)], am1 > 0.0);
+        return dx_inv * (fm * am + w3 * (fp1 - fm1) * (ap1 - am1));
+    } else if (kind == 2) {
+        double as = q * q * a_sq(F, finest_index(P, i));
+        double am = dp_inv * cc * (gamma_(P, momentum(P, j + 1), as) - gamma_(P, momentum(P, j), as));
+        return dx_inv * (am > 0.0 ? f[NS(P, i - 1, j)] : f[NS(P, i, j)]) * am;
+    }
+    double as_1 = q * q * a_sq(F, finest_index(P, i)), as_2 = q * q * a_sq(F, finest_index(P, i + 1));
+    double Em = q * patch_efield(P, F, i), mom = momentum(P, j);
+    double am = Em - cc * dx_inv * (gamma_(P, mom, as_2) - gamma_(P, mom, as_1));
+    if (kind == 3) return dp_inv * (am > 0.0 ? f[NS(P, i, j - 1)] : f[NS(P, i, j)]) * am;
+    double as_0 = q * q * a_sq(F, finest_index(P, i - 1)), as_3 = q * q * a_sq(F, finest_index(P, i + 2));
+    double Ep1 = q * patch_efield(P, F, i + 1), Em1 = q * patch_efield(P, F, i - 1);
+    double ap1 = Ep1 - cc * dx_inv * (gamma_(P, mom, as_3) - gamma_(P, mom, as_2));
+    double am1 = Em1 - cc * dx_inv * (gamma_(P, mom, as_1) - gamma_(P, mom, as_0));
+    double fm = vo_weno(f[NS(P, i, j - 2)], f[NS(P, i, j - 1)], f[NS(P, i, j)], f[NS(P, i, j + 1)], am > 0.0);
+    double fp1 = vo_weno(f[NS(P, i + 1, j - 2)], f[NS(P, i + 1, j - 1)], f[NS(P, i + 1, j)], f[NS(P, i + 1, j + 1)], ap1 > 0.0);
+    double fm1 = vo_weno(f[NS(P, i - 1, j - 2)], f[NS(P, i - 1, j - 1)], f[NS(P, i - 1, j)], f[NS(P, i - 1, j + 1)], am1 > 0.0);
+    return dp_inv * (fm * am + w3 * (fp1 - fm1) * (ap1 - am1));
+}
+/* the four flux loops of sub-step 0 at faces flagged is_interrior_level_boundary_{x,p} (Rectangle.cpp:1313-1394):
+ * called between the unflagged flux evaluation and the RK combination */
+static void replace_level_boundary_fluxes(vo_mesh* M, const vo_fields* F, int p, int step) {
+    vo_patch* P = M->P[p]; vo_conn* c = &M->C[p];
+    const int nx = P->n_x, np = P->n_p; const long npad = (long)(nx + 4) * (np + 4);
+    double* FxHs = P->FxH + step * npad; double* FpHs = P->FpH + step * npad;
+    for (int i = 0; i < nx + 1; i++)
+        for (int j = -1; j < np + 1; j++) {
+            long idx = NS(P, i, j);
+            if (c->flags[idx] & VO_LBX) {
+                FxHs[idx] = flux_to_coarse(M, F, c->finer_x[idx], P->x_pos + i, P->p_pos + j, 0);
+                if (step == 0) P->FxL[idx] = flux_to_coarse(M, F, c->finer_x[idx], P->x_pos + i, P->p_pos + j, 2);
+            }
+        }
+    for (int i = -1; i < nx + 1; i++)
+        for (int j = 0; j < np + 1; j++) {
+            long idx = NS(P, i, j);
+            if (c->flags[idx] & VO_LBP) {
+                FpHs[idx] = flux_to_coarse(M, F, c->finer_p[idx], P->x_pos + i, P->p_pos + j, 1);
+                if (step == 0) P->FpL[idx] = flux_to_coarse(M, F, c->finer_p[idx], P->x_pos + i, P->p_pos + j, 3);
+            }
+        }
+}
+static void replace_level_boundary_fluxes_hook(void* M, const vo_fields* F, int p, int step) {
+    replace_level_boundary_fluxes((vo_mesh*)M, F, p, step);
+}
+/* Level::FCTTimeStep (Level.cpp:12-17) */
+void vo_mesh_substep(vo_mesh* M, const vo_fields* F, int depth, double dt, int step, int subStep) {
+    for (int a = M->level_start[depth]; a < M->level_start[depth + 1]; a++)
+        fct_substep_impl(M->P[M->order[a]], F, dt, step, subStep, M, M->order[a]);
+}
+
+/* ---- limiter sync: Mesh::PushBoundaryC (Mesh.cpp:904-917) ------------------------------------------------- */
+/* Rectangle::SetCFromSameLevel (Rectangle.cpp:1795-1833): n = this (the neighbour), c = rectangle (the caller) */
+static void set_c_from_same_level(vo_mesh* M, int n, int i, int j, int c, int t) {
+    if (n < 0) return;   /* BoundaryCondition: value-initialised, refinementRatio = 0 -> zero-trip loops (quirk Q8) */
+    vo_patch *N = M->P[n], *Cl = M->P[c]; const int r = M->r;
+    int in = i - N->x_pos, jn = j - N->p_pos, icl = i - Cl->x_pos, jcl = j - Cl->p_pos;
+    for (int k = 0; k < r; k++) {
+        if (t == 0) {
+            double cx = N->FxDS[NS(N, in, jn + k)] > 0.0 ? fmin(Cl->Rp[NS(Cl, icl, jcl + k)], N->Rm[NS(N, in - 1, jn + k)])
+                                                          : fmin(N->Rp[NS(N, in - 1, jn + k)], Cl->Rm[NS(Cl, icl, jcl + k)]);
+            N->Cx[NS(N, in, jn + k)] = cx; Cl->Cx[NS(Cl, icl, jcl + k)] = cx;
+        } else if (t == 1) {
+            double cx = N->FxDS[NS(N, in, jn + k)] > 0.0 ? fmin(Cl->Rm[NS(Cl, icl - 1, jcl + k)], N->Rp[NS(N, in, jn + k)])
+                                                          : fmin(N->Rm[NS(N, in, jn + k)], Cl->Rp[NS(Cl, icl - 1, jcl + k)]);
+            N->Cx[NS(N, in, jn + k)] = cx; Cl->Cx[NS(Cl, icl, jcl + k)] = cx;
+        } else if (t == 2) {
+            double cp = N->FpDS[NS(N, in + k, jn)] > 0.0 ? fmin(Cl->Rp[NS(Cl, icl + k, jcl)], N->Rm[NS(N, in + k, jn - 1)])
+                                                          : fmin(N->Rp[NS(N, in + k, jn - 1)], Cl->Rm[NS(Cl, icl + k, jcl)]);
+            N->Cp[NS(N, in + k, jn)] = cp; Cl->Cp[NS(Cl, icl + k, jcl)] = cp;
+        } else {
+            double cp = N->FpDS[NS(N, in + k, jn)] > 0.0 ? fmin(Cl->Rm[NS(Cl, icl + k, jcl - 1)], N->Rp[NS(N, in + k, jn)])
+                                                          : fmin(N->Rm[NS(N, in + k, jn)], Cl->Rp[NS(Cl, icl + k, jcl - 1)]);
+            N->Cp[NS(N, in + k, jn)] = cp; Cl->Cp[NS(Cl, icl + k, jcl)] = cp;
+        }
+    }
+}
+/* Rectangle::UpdateCFromSameLevel (Rectangle.cpp:1879-1917) */
+static void update_c_from_same_level(vo_mesh* M, int n, int i, int j, int c, int t) {
+    if (n < 0) return;
+    vo_patch *N = M->P[n], *Cl = M->P[c]; const int r = M->r;
+    int in = i - N->x_pos, jn = j - N->p_pos, icl = i - Cl->x_pos, jcl = j - Cl->p_pos;
+    for (int k = 0; k < r; k++) {
+        if (t < 2) {
+            double cx = fmin(N->Cx[NS(N, in, jn + k)], Cl->Cx[NS(Cl, icl, jcl + k)]);
+            N->Cx[NS(N, in, jn + k)] = cx; Cl->Cx[NS(Cl, icl, jcl + k)] = cx;
+        } else {
+            double cp = fmin(N->Cp[NS(N, in + k, jn)], Cl->Cp[NS(Cl, icl + k, jcl)]);
+            N->Cp[NS(N, in + k, jn)] = cp; Cl->Cp[NS(Cl, icl + k, jcl)] = cp;
+        }
+    }
+}
+/* Rectangle::SetCFromDifferentLevel (Rectangle.cpp:1625-1704): n = this (coarse), c = rectangle (the fine caller) */
+static void set_c_from_different_level(vo_mesh* M, int n, int i, int j, int c, int t) {
+    vo_patch *N = M->P[n], *Cl = M->P[c]; const int r = M->r;
+    int icl = i - Cl->x_pos, jcl = j - Cl->p_pos, ico = i / r - N->x_pos, jco = j / r - N->p_pos;
+    if (t == 0) {
+        double cx = N->Cx[NS(N, ico, jco)];
+        for (int k = 0; k < r; k++) cx = fmin(cx, Cl->FxDS[NS(Cl, icl, jcl + k)] > 0.0 ? Cl->Rp[NS(Cl, icl, jcl + k)] : Cl->Rm[NS(Cl, icl, jcl + k)]);
+        cx = fmin(cx, N->FxDS[NS(N, ico, jco)] > 0.0 ? N->Rm[NS(N, ico - 1, jco)] : N->Rp[NS(N, ico - 1, jco)]);
+        for (int k = 0; k < r; k++) Cl->Cx[NS(Cl, icl, jcl + k)] = cx;
+        N->Cx[NS(N, ico, jco)] = cx;
+    } else if (t == 1) {
+        double cx = N->Cx[NS(N, ico, jco)];
+        for (int k = 0; k < r; k++) cx = fmin(cx, Cl->FxDS[NS(Cl, icl, jcl + k)] > 0.0 ? Cl->Rm[NS(Cl, icl - 1, jcl + k)] : Cl->Rp[NS(Cl, icl - 1, jcl + k)]);
+        cx = fmin(cx, N->FxDS[NS(N, ico, jco)] > 0.0 ? N->Rp[NS(N, ico, jco)] : N->Rm[NS(N, ico, jco)]);
+        for (int k = 0; k < r; k++) Cl->Cx[NS(Cl, icl, jcl + k)] = cx;
+        N->Cx[NS(N, ico, jco)] = cx;
+    } else if (t == 2) {
+        double cp = N->Cp[NS(N, ico, jco)];
+        for (int k = 0; k < r; k++) cp = fmin(cp, Cl->FpDS[NS(Cl, icl + k, jcl)] > 0.0 ? Cl->Rp[NS(Cl, icl + k, jcl)] : Cl->Rm[NS(Cl, icl + k, jcl)]);
+        cp = fmin(cp, N->FpDS[NS(N, ico, jco)] > 0.0 ? N->Rm[NS(N, ico, jco - 1)] : N->Rp[NS(N, ico, jco - 1)]);
+        for (int k = 0; k < r; k++) Cl->Cp[NS(Cl, icl + k, jcl)] = cp;
+        N->Cp[NS(N, ico, jco)] = cp;
+    } else {
+        double cp = N->Cp[NS(N, ico, jco)];
+        for (int k = 0; k < r; k++) cp = fmin(cp, Cl->FpDS[NS(Cl, icl + k, jcl)] > 0.0 ? Cl->Rm[NS(Cl, icl + k, jcl - 1)] : Cl->Rp[NS(Cl, icl + k, jcl - 1)]);
+        cp = fmin(cp, N->FpDS[NS(N, ico, jco)] > 0.0 ? N->Rp[NS(N, ico, jco)] : N->Rm[NS(N, ico, jco)]);
+        for (int k = 0; k < r; k++) Cl->Cp[NS(Cl, icl + k, jcl)] = cp;
+        N->Cp[NS(N, ico, jco)] = cp;
+    }
+}
+/* CalculateSameBoundaryC / CalculateDifferentBoundaryC / UpdateSameBoundaryC (Rectangle.cpp:1835-1877, 1706-1763, 1919-1960) */
+static void boundary_c_pass(vo_mesh* M, int p, int pass) {
+    vo_patch* P = M->P[p]; vo_conn* c = &M->C[p]; const int r = M->r;
+    const int n_x = P->n_x, n_p = P->n_p, x_pos = P->x_pos, p_pos = P->p_pos;
+    for (int side = 0; side < 4; side++) {
+        const int ns = side < 2 ? c->ns_x - 2 : c->ns_p;
+        for (int i = 0; i < ns; i++) {
+            const int e = side < 2 ? i + 1 : i;
+            const int same = c->same[side][e], nb = c->nb[side][e];
+            int gi, gj;
+            if (side == 0) { gi = x_pos; gj = p_pos + r * i; }
+            else if (side == 1) { gi = x_pos + n_x; gj = p_pos + r * i; }
+            else if (side == 2) { gi = x_pos + r * i; gj = p_pos; }
+            else { gi = x_pos + r * i; gj = p_pos + n_p; }
+            if (pass == 4 && same) set_c_from_same_level(M, nb, gi, gj, p, side);
+            else if (pass == 5 && !same) set_c_from_different_level(M, nb, gi, gj, p, side);
+            else if (pass == 6 && same) update_c_from_same_level(M, nb, gi, gj, p, side);
+        }
+    }
+}
+void vo_mesh_push_boundary_c(vo_mesh* M) {
+    for (int pass = 4; pass <= 6; pass++)
+        for (int l = 0; l < M->n_levels; l++)
+            for (int a = M->level_start[l]; a < M->level_start[l + 1]; a++) boundary_c_pass(M, M->order[a], pass);
+}
+/* Mesh::Advance (Mesh.cpp:64-89) */
+void vo_mesh_advance(vo_mesh* M, const vo_fields* F, double dt, int step) {
+    const int nl = M->n_levels;
+    for (int i = nl - 1; i > -1; i--) vo_mesh_substep(M, F, i, dt, step, 0);
+    vo_mesh_push_data(M, 2);
+    for (int i = nl - 1; i > -1; i--) vo_mesh_substep(M, F, i, dt, step, 1);
+    vo_mesh_push_boundary_c(M);
+    for (int i = nl - 1; i > -1; i--) vo_mesh_substep(M, F, i, dt, step, 2);
+    vo_mesh_push_data(M, 1);
+    if (step == 5) for (int i = nl - 1; i > -1; i--) vo_mesh_substep(M, F, i, dt, step, 3);
+}
+/* Mesh::InterpolateRhoAndJToFinestMesh (Mesh.cpp:52-56) -> Level::CollectRhoAndJ (Level.cpp:19-62): adds this species'
+ * moments to charge_s[N] and J[N].  scratch: 4*N doubles. */
+void vo_mesh_moments(vo_mesh* M, const vo_fields* F, double* charge_s, double* J, double* scratch) {
+    const int N = F->x_size;
+    double *chargeL = scratch, *currentL = scratch + N, *cR = scratch + 2 * N, *jR = scratch + 3 * N;
+    for (int l = 0; l < M->n_levels; l++) {
+        for (int i = 0; i < N; i++) { chargeL[i] = 0.0; currentL[i] = 0.0; }
+        for (int a = M->level_start[l]; a < M->level_start[l + 1]; a++) {
+            int p = M->order[a]; vo_patch* P = M->P[p];
+            vo_patch_moments(P, F, M->C[p].flags, cR, jR);
+            int n = P->n_x * P->rtb, shift = P->x_pos * P->rtb;
+            for (int j = 0; j < n; j++) { chargeL[shift + j] += cR[j]; currentL[shift + j] += jR[j]; }
+        }
+        for (int i = 0; i < N; i++) { charge_s[i] += chargeL[i]; J[i] += currentL[i]; }
+    }
 }

@@ -27,6 +27,12 @@ CASES = {
     "single_128x64_steps": (128, 64, 1, 2.0, 6, ["threads=1"]),
     # unequal species resolution
     "single_96x48x24_steps": (96, 48, 1, 0.5, 3, ["np_ion=24", "pre_steps=1600", "threads=1"]),
+    # 2-level AMR (BASELINE config 2 shape: coarse 64x32, one fine patch), per-stage records with PHI for injection
+    "amr2_64x32_stages": (64, 32, 2, 0.5, 1, ["stage_dumps=1", "pre_steps=1600", "threads=1"]),
+    # 3-level AMR with regridding every 2 steps (BASELINE config 4 shape): up to 6 adjacent finest patches
+    "amr3_48x32_regrid": (48, 32, 3, 0.5, 9, ["pre_steps=1600", "regrid_every=2", "threads=1"]),
+    # 2-level AMR, refinement forced in the high-momentum tail (config 2: "AMR in the high-momentum tail")
+    "amr2_tail_64x48_steps": (64, 48, 2, 0.3, 3, ["pre_steps=1700", "refine_mode=1", "tail_p0=1", "threads=1"]),
 }
 
 
@@ -44,9 +50,11 @@ def reduce(records):
     return out
 
 
-def main():
+def main(only=None):
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], stdout=subprocess.DEVNULL)
     for name, (nx, np_, lf, dens, steps, extra) in CASES.items():
+        if only and name not in only:
+            continue
         with tempfile.TemporaryDirectory() as tmp:
             path = os.path.join(tmp, "dump.bin")
             cmd = [HARNESS, path, str(nx), str(np_), str(lf), str(dens), str(steps)] + extra
@@ -58,4 +66,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1:])

@@ -82,3 +82,61 @@ def test_particle_number_conserved_by_port():
         O.advance(dt)
     for s in range(2):
         assert abs(O.patches[s].f1[2:-2, 2:-2].sum() - n0[s]) <= 1e-13 * abs(n0[s])
+
+
+# ---- AMR: multi-level, multi-patch meshes ------------------------------------------------
+def make_mesh_oracle(d, tag, poisson):
+    from oracle.port import MeshOracle, hierarchy_from_dump
+    mt = meta(d)
+    sp = species_from(d)
+    case = load_product()
+    laser = lambda t: (case.vrt_case_laser_by(mt["lam"], mt["amp"], 0.0, t), case.vrt_case_laser_bz(mt["lam"], mt["amp"], 0.0, t))
+    H = hierarchy_from_dump(d, tag)
+    maxd = mt["Lfinest"] - 1
+    O = MeshOracle(mt["nx"] * 2 ** maxd, mt["dx"], sp, H, r=2, max_depth=maxd, laser=laser, poisson=poisson)
+    return O, H, mt
+
+
+def test_amr_port_bit_identical_per_stage_with_injected_phi():
+    """2-level mesh: every stage of Mesh::Advance incl. coarse-fine flux matching, ghost interpolation, restriction,
+    limiter sync and the rtb = 2 moments, bit for bit against the reference (ghost cells included)."""
+    d = load_golden("amr2_64x32_stages")
+    O, H, mt = make_mesh_oracle(d, "step0", poisson=False)
+    assert [len(h) for h in H] == [2, 2]
+    O.load_reference_state(d, "step0")
+    dt = float(d["step1/dt"][0])
+    for i in range(6):
+        tag = f"step1_stage{i}"
+        O.stage(dt, i, phi_inject=d[tag + "/PHI"])
+        for s in range(2):
+            for P, dd in zip(O.patches[s], H[s]):
+                assert np.array_equal(P.f1, d[f"{tag}/{dd['key']}/f1"]), (tag, dd["key"])
+        for k in ("By", "Bz", "Ey", "Ez", "Ay", "Az", "a_squared", "J", "charge"):
+            assert np.array_equal(O.fields.a[k], d[tag + "/" + k]), (tag, k)
+
+
+@pytest.mark.parametrize("name", ["amr3_48x32_regrid", "amr2_tail_64x48_steps"])
+def test_amr_port_per_step_from_reference_state(name):
+    """Protocol P1 on AMR hierarchies (3 levels, regridded every 2 steps, up to 6 adjacent finest patches): one step from
+    each reference state whose hierarchy survives the step."""
+    from oracle.port import hierarchy_from_dump
+    d = load_golden(name)
+    mt = meta(d)
+    compared, most = 0, 0
+    for n in range(1, mt["steps"] + 1):
+        strip = lambda H: [[{k: v for k, v in p.items()} for p in h] for h in H]
+        if strip(hierarchy_from_dump(d, f"step{n - 1}")) != strip(hierarchy_from_dump(d, f"step{n}")):
+            continue   # the reference regridded at the end of this step: its dump is on another hierarchy
+        O, H, _ = make_mesh_oracle(d, f"step{n - 1}", poisson=True)
+        O.load_reference_state(d, f"step{n - 1}")
+        O.advance(float(d[f"step{n}/dt"][0]))
+        for s in range(2):
+            for P, dd in zip(O.patches[s], H[s]):
+                assert rel_l2(P.f1, d[f"step{n}/{dd['key']}/f1"]) < 1e-13, (n, dd["key"])
+        for k in ("Ey", "Ez", "By", "Bz", "Ay", "Az"):
+            assert rel_l2(O.fields.a[k][0], d[f"step{n}/{k}"][0]) < 1e-13
+        compared += 1
+        most = max(most, max(len(h) for h in H))
+    assert compared >= 3
+    if name == "amr3_48x32_regrid":
+        assert most >= 6   # the fixture must exercise same-level neighbours
