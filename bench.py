@@ -174,14 +174,8 @@ def main():
                             graph=not args.no_graph)
     ctx = run.ctx
     if n_gpus > 1:
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            buf = (__import__("ctypes").c_ubyte * 128)()
-            assert run.L.vrt_nccl_unique_id(buf) == 0
-            uid = torch.tensor(list(buf), dtype=torch.uint8, device="cuda")
-        dist.broadcast(uid, 0)
-        raw = bytes(uid.cpu().tolist())
-        ctx.call("vrt_comm_init", raw, rank, n_gpus)
+        from veritas_b200.parallel import broadcast_unique_id
+        ctx.call("vrt_comm_init", broadcast_unique_id(dist, run.L, rank, device="cuda"), rank, n_gpus)
     run.init_device()
     if not args.skip_fields_phase:
         run.run_fields_phase()          # veritas.cpp:139-144: the laser enters the box while the plasma is frozen

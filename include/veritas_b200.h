@@ -35,6 +35,10 @@ enum { VRT_EX0 = 0, VRT_TIME = 1 };
 enum { VRT_PATH_AUTO = 0, VRT_PATH_SPLIT = 1 /* sub-step kernels with ghost syncs, any hierarchy */,
        VRT_PATH_FUSED = 2 /* one streaming pass per stage; single-level full-domain patches / x-slabs */ };
 
+/* work-plane selectors for vrt_patch_download_plane (Rectangle.hpp:7: FxH, FpH, FxL, FpL, FxDS, FpDS, Rp, Rm, Cx, Cp, ex, ep, fx, fp) */
+enum { VRT_PLANE_FXH = 0, VRT_PLANE_FPH, VRT_PLANE_FXL, VRT_PLANE_FPL, VRT_PLANE_FXDS, VRT_PLANE_FPDS, VRT_PLANE_RP, VRT_PLANE_RM,
+       VRT_PLANE_CX, VRT_PLANE_CP, VRT_PLANE_EX, VRT_PLANE_EP, VRT_PLANE_FX, VRT_PLANE_FP };
+
 /* Rectangle ctor arguments (Rectangle.hpp:23): depth 0 = finest level. */
 typedef struct {
     int depth, x_pos, p_pos, n_x, n_p;
@@ -58,8 +62,9 @@ int vrt_set_grid(vrt_ctx* ctx, int x_size_finest, double dx_finest, int n_prepad
                  int refinement_ratio, int max_depth);
 int vrt_set_species(vrt_ctx* ctx, int s, double mass, double charge, double pmin, double dp_finest);
 /* Mesh::promoteHierarchyToMesh (Mesh.cpp:794-875): (re)create the patches of species s.  Connectivity
- * (Rectangle::CalculateConnectivitySame / FromFiner, Rectangle.cpp:671-864) is derived from the descriptors.
- * Patch data are zero after this call. */
+ * (Rectangle::CalculateConnectivitySame / FromFiner, Rectangle.cpp:671-864) is derived from the descriptors; it depends
+ * on the order of the patches inside a level, which must be the order of Level::rectangles.  Patches of refined levels
+ * (depth < max_depth) must start on multiples of the refinement ratio.  Patch data are zero after this call. */
 int vrt_set_hierarchy(vrt_ctx* ctx, int s, int n_patches, const vrt_patch_desc* patches);
 int vrt_set_path(vrt_ctx* ctx, int path);
 int vrt_get_path(vrt_ctx* ctx, int s);
@@ -68,6 +73,8 @@ int vrt_get_path(vrt_ctx* ctx, int s);
 /* state: 0 = f^n, 1 = current stage value, 2 = low-order predictor (Rectangle.hpp:96-98). */
 int vrt_patch_upload_f(vrt_ctx* ctx, int s, int patch, int state, const double* host_padded);
 int vrt_patch_download_f(vrt_ctx* ctx, int s, int patch, int state, double* host_padded);
+/* One work plane of a patch in the padded layout (split path; diagnostics and parity tests). slot: RK slot for FxH/FpH. */
+int vrt_patch_download_plane(vrt_ctx* ctx, int s, int patch, int which, int slot, double* host_padded);
 /* Rectangle::FCTTimeStep(…,3) applied to every patch (Mesh.cpp:869-874): f0 := f1 on the padded array. */
 int vrt_commit_state(vrt_ctx* ctx, int s);
 int vrt_field_upload(vrt_ctx* ctx, int which, int slot, const double* host);   /* M = x_size+pads doubles */
@@ -114,6 +121,17 @@ int vrt_set_option(vrt_ctx* ctx, int option, int value);
  * (Settings::InitialDistribution, veritas.cpp:107-115), evaluated on the device: sub-cell midpoint quadrature
  * with r^(depth+quadrature_depth) points per direction; writes states 0 and 1.  SURVEY.md §8(f) item 2. */
 int vrt_init_maxwellian_slab(vrt_ctx* ctx, int s, double xl, double xr, double n0, double T, int quadrature_depth);
+
+/* ---- hierarchy connectivity on the host (no device needed) ---------------------------------------- */
+/* The tables Rectangle::CalculateConnectivitySame / CalculateConnectivityFromFiner build (Rectangle.cpp:671-864), as
+ * vrt_set_hierarchy derives them.  side: 0 xm, 1 xp (n_p/r + 2 strips, first and last = the 2-cell corners), 2 pm, 3 pp
+ * (n_x/r strips).  nb = neighbour patch number in the caller's numbering, -1 = the BoundaryCondition object;
+ * same = is_exterrior_boundary_same_level_*.  flags per padded cell: 1 is_nested, 2 / 4 is_interrior_level_boundary_x / _p. */
+typedef struct vrt_conn vrt_conn;
+int vrt_conn_create(vrt_conn** out, int n_patches, const vrt_patch_desc* patches, int refinement_ratio, int max_depth);
+int vrt_conn_strips(const vrt_conn* conn, int patch, int side, int* nb, unsigned char* same);   /* returns the strip count */
+int vrt_conn_flags(const vrt_conn* conn, int patch, unsigned char* flags_padded);
+void vrt_conn_destroy(vrt_conn* conn);
 
 /* ---- multi-GPU x-slabs (no counterpart in the reference) ------------------- */
 /* This context owns finest columns [x_begin, x_end) of every full-domain single-level patch. */

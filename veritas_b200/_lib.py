@@ -41,7 +41,12 @@ SIGNATURES = {
     "vrt_get_path": (C.c_int, [C.c_void_p, C.c_int]),
     "vrt_patch_upload_f": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, dbl_p]),
     "vrt_patch_download_f": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, dbl_p]),
+    "vrt_patch_download_plane": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, dbl_p]),
     "vrt_commit_state": (C.c_int, [C.c_void_p, C.c_int]),
+    "vrt_conn_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(PatchDesc), C.c_int, C.c_int]),
+    "vrt_conn_strips": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_ubyte)]),
+    "vrt_conn_flags": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_ubyte)]),
+    "vrt_conn_destroy": (None, [C.c_void_p]),
     "vrt_field_upload": (C.c_int, [C.c_void_p, C.c_int, C.c_int, dbl_p]),
     "vrt_field_download": (C.c_int, [C.c_void_p, C.c_int, C.c_int, dbl_p]),
     "vrt_set_1d": (C.c_int, [C.c_void_p, C.c_int, dbl_p]),

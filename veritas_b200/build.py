@@ -20,6 +20,7 @@ UNITS = [
     ("vrt_abi.cu", []),
     ("vrt_fields.cu", ["-fmad=false"]),
     ("vrt_split.cu", ["-fmad=false"]),
+    ("vrt_amr.cu", ["-fmad=false"]),
     ("vrt_fused.cu", []),
     ("vrt_init.cu", []),
     ("vrt_comm.cu", []),

@@ -38,6 +38,8 @@ void free_species(VrtSpeciesState& S) {
     for (double* p : S.allocations) cudaFree(p);
     S.allocations.clear();
     if (S.d_patches) { cudaFree(S.d_patches); S.d_patches = nullptr; }
+    if (S.conn_pool) { cudaFree(S.conn_pool); S.conn_pool = nullptr; }
+    S.has_amr = false;
     S.patches.clear(); S.level_patches.clear(); S.desc.clear();
     S.configured = false;
 }
@@ -117,13 +119,17 @@ int vrt_set_grid(vrt_ctx* c, int N, double dx, int pre, int post, int r, int max
     VrtFields& F = c->F;
     F.N = N; F.pre = pre; F.post = post; F.M = N + pre + post; F.dx = dx;
     c->refinement_ratio = r; c->max_depth = max_depth;
+    // the coarse-fine flux matching recurses once per level (vrt_amr.cu: rgk_flux, 280-byte frames)
+    if (max_depth >= 2) cudaDeviceSetLimit(cudaLimitStackSize, 1024 + 384 * (size_t)max_depth);
     int rc;
     for (int v = 0; v < 6; v++) if ((rc = dev_alloc(c, c->field_allocs, &F.Y[v], 8L * F.M))) return rc;
     if ((rc = dev_alloc(c, c->field_allocs, &F.a_squared, N + 1))) return rc;
     if ((rc = dev_alloc(c, c->field_allocs, &F.a_squared0, N + 1))) return rc;
     if ((rc = dev_alloc(c, c->field_allocs, &F.PHI, N))) return rc;
-    if ((rc = dev_alloc(c, c->field_allocs, &F.E, N + 4))) return rc;
-    if ((rc = dev_alloc(c, c->field_allocs, &F.E0, N + 4))) return rc;
+    F.epad = std::max(2, (int)std::lround(std::pow((double)r, max_depth)));
+    if (!check(c, F.epad < N / 2, "vrt_set_grid: too many levels for this x size")) return VRT_ERR_ARG;
+    if ((rc = dev_alloc(c, c->field_allocs, &F.E, N + 2 * F.epad))) return rc;
+    if ((rc = dev_alloc(c, c->field_allocs, &F.E0, N + 2 * F.epad))) return rc;
     if ((rc = dev_alloc(c, c->field_allocs, &F.charge, N))) return rc;
     if ((rc = dev_alloc(c, c->field_allocs, &F.J, N))) return rc;
     if ((rc = dev_alloc(c, c->field_allocs, &F.neutral, N))) return rc;
@@ -177,7 +183,7 @@ int vrt_set_hierarchy(vrt_ctx* c, int s, int n_patches, const vrt_patch_desc* d)
     const int r = c->refinement_ratio;
     for (int p = 0; p < n_patches; p++) {
         const vrt_patch_desc& q = d[p];
-        if (!check(c, q.depth >= 0 && q.depth <= c->max_depth && q.n_x >= 4 && q.n_p >= 4 && q.n_x % r == 0 && q.n_p % r == 0,
+        if (!check(c, q.depth >= 0 && q.depth <= c->max_depth && q.n_x >= r && q.n_p >= r && q.n_x % r == 0 && q.n_p % r == 0,
                    "vrt_set_hierarchy: bad patch descriptor")) return VRT_ERR_ARG;
     }
     S.desc.assign(d, d + n_patches);
@@ -218,9 +224,12 @@ int vrt_set_hierarchy(vrt_ctx* c, int s, int n_patches, const vrt_patch_desc* d)
     // the device table is grouped by depth so that one level is a contiguous range; S.patches is indexed by
     // the caller's patch number, table_index maps it into the table
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return d[a].depth < d[b].depth; });
+    vrt_conn conn;
+    if (vrt_conn_derive(conn, n_patches, d, r, c->max_depth)) { c->err = "vrt_set_hierarchy: " + conn.err; return VRT_ERR_ARG; }
     S.patches.resize(n_patches);
     std::vector<VrtPatchDev> table(n_patches);
     S.table_index.assign(n_patches, 0);
+    S.table_order = order;
     for (int ti = 0; ti < n_patches; ti++) {
         const int p = order[ti];
         const vrt_patch_desc& q = d[p];
@@ -241,6 +250,7 @@ int vrt_set_hierarchy(vrt_ctx* c, int s, int n_patches, const vrt_patch_desc* d)
         S.level_patches[q.depth].push_back(ti);
     }
     S.table = table;
+    if ((rc = vrt_amr_upload_connectivity(c, s, conn))) return rc;
     VRT_CUDA(c, cudaMalloc(&S.d_patches, sizeof(VrtPatchDev) * n_patches));
     VRT_CUDA(c, cudaMemcpyAsync(S.d_patches, S.table.data(), sizeof(VrtPatchDev) * n_patches, cudaMemcpyHostToDevice, c->stream));
     VRT_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -321,6 +331,35 @@ int vrt_commit_state(vrt_ctx* c, int s) {
     return 0;
 }
 
+int vrt_patch_download_plane(vrt_ctx* c, int s, int patch, int which, int slot, double* host) {
+    if (!c || !host) return VRT_ERR_ARG;
+    if (!check(c, s >= 0 && s < c->n_species && patch >= 0 && patch < (int)c->S[s].desc.size() && slot >= 0 && slot < 6, "vrt_patch_download_plane: bad arguments")) return VRT_ERR_ARG;
+    if (!check(c, c->S[s].path == VRT_PATH_SPLIT, "vrt_patch_download_plane: work planes exist on the split path only")) return VRT_ERR_STATE;
+    cudaSetDevice(c->device);
+    const VrtPatchDev& P = c->S[s].patches[patch];
+    const double* src = nullptr;
+    switch (which) {
+        case VRT_PLANE_FXH: src = P.FxH + (long)slot * P.npad; break;
+        case VRT_PLANE_FPH: src = P.FpH + (long)slot * P.npad; break;
+        case VRT_PLANE_FXL: src = P.FxL; break;
+        case VRT_PLANE_FPL: src = P.FpL; break;
+        case VRT_PLANE_FXDS: src = P.FxDS; break;
+        case VRT_PLANE_FPDS: src = P.FpDS; break;
+        case VRT_PLANE_RP: src = P.Rp; break;
+        case VRT_PLANE_RM: src = P.Rm; break;
+        case VRT_PLANE_CX: src = P.Cx; break;
+        case VRT_PLANE_CP: src = P.Cp; break;
+        case VRT_PLANE_EX: src = P.ex; break;
+        case VRT_PLANE_EP: src = P.ep; break;
+        case VRT_PLANE_FX: src = P.fx; break;
+        case VRT_PLANE_FP: src = P.fp; break;
+        default: c->err = "vrt_patch_download_plane: bad selector"; return VRT_ERR_ARG;
+    }
+    VRT_CUDA(c, cudaMemcpyAsync(host, src, sizeof(double) * P.npad, cudaMemcpyDeviceToHost, c->stream));
+    VRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 int vrt_field_upload(vrt_ctx* c, int which, int slot, const double* host) {
     if (!c || !host || which < 0 || which > 5 || slot < 0 || slot > 7 || !c->grid_set) return VRT_ERR_ARG;
     cudaSetDevice(c->device);
@@ -345,7 +384,7 @@ static double* sel_1d(vrt_ctx* c, int which, long* n) {
         case VRT_J: return F.J;
         case VRT_A_SQUARED: *n = F.N + 1; return F.a_squared;
         case VRT_NEUTRALIZATION: return F.neutral;
-        case VRT_EFIELD: return F.E + 2;
+        case VRT_EFIELD: return F.E + F.epad;
         default:
             if (which >= VRT_CHARGES0 && which < VRT_CHARGES0 + c->n_species) return c->S[which - VRT_CHARGES0].d_charges;
     }
@@ -426,11 +465,7 @@ int vrt_poisson(vrt_ctx* c) { if (int r = ready(c)) return r; return vrt_fields_
 static int push_data_impl(vrt_ctx* c, int s, int val) {
     VrtSpeciesState& S = c->S[s];
     if (S.path == VRT_PATH_FUSED) return 0;   // ghosts of the slab planes are never written; halos are exchanged per stage
-    // Mesh::PushData (Mesh.cpp:91-106).  Single-level hierarchies: every neighbour is the BoundaryCondition object.
-    if (!check(c, c->max_depth == 0 || S.desc.size() == 1, "vrt_push_data: multi-patch hierarchies are not supported yet")) return VRT_ERR_STATE;
-    for (size_t d = 0; d < S.level_patches.size(); d++)
-        if (int r = vrt_split_fill_domain_ghosts(c, s, (int)d, val)) return r;
-    return 0;
+    return vrt_amr_push_data(c, s, val);   // Mesh::PushData (Mesh.cpp:91-106)
 }
 
 static int vlasov_stage_impl(vrt_ctx* c, int s, const double* d_dt, int step) {
@@ -445,7 +480,7 @@ static int vlasov_stage_impl(vrt_ctx* c, int s, const double* d_dt, int step) {
     for (int d = nl - 1; d >= 0; d--) if ((r = vrt_split_substep(c, s, d, d_dt, step, 0))) return r;
     if ((r = push_data_impl(c, s, 2))) return r;
     for (int d = nl - 1; d >= 0; d--) if ((r = vrt_split_substep(c, s, d, d_dt, step, 1))) return r;
-    // Mesh::PushBoundaryC: zero-trip loops when every neighbour is the BoundaryCondition object (quirk Q8)
+    if ((r = vrt_amr_push_boundary_c(c, s))) return r;
     for (int d = nl - 1; d >= 0; d--) if ((r = vrt_split_substep(c, s, d, d_dt, step, 2))) return r;
     if ((r = push_data_impl(c, s, 1))) return r;
     if (step == 5) for (int d = nl - 1; d >= 0; d--) if ((r = vrt_split_substep(c, s, d, d_dt, step, 3))) return r;
@@ -476,7 +511,8 @@ int vrt_push_data(vrt_ctx* c, int s, int val) {
 int vrt_push_boundary_c(vrt_ctx* c, int s) {
     if (int r = ready(c)) return r;
     if (!check(c, s >= 0 && s < c->n_species, "vrt_push_boundary_c: bad arguments")) return VRT_ERR_ARG;
-    return 0;   // single-patch levels: all limiter-sync loops have zero trip count (quirk Q8)
+    if (c->S[s].path == VRT_PATH_FUSED) return 0;   // the fused kernel carries the limiter across its own tiles
+    return vrt_amr_push_boundary_c(c, s);
 }
 
 int vrt_field_stage(vrt_ctx* c, int step, double dt, double by0, double bz0) {

@@ -1,0 +1,572 @@
+// AMR machinery of the split path: everything Mesh::PushData (Mesh.cpp:91-106),
+// Mesh::PushBoundaryC (Mesh.cpp:904-917) and the coarse-fine flux matching of Rectangle::FCTTimeStep sub-step 0
+// (Rectangle.cpp:1313-1394) do between the sub-step kernels of vrt_split.cu.
+//
+//   host   vrt_conn_derive            Rectangle::CalculateConnectivitySame / FromFiner   Rectangle.cpp:671-864
+//   K3     k_ghost_same               Rectangle::UpdateSameLevelBoundaries               Rectangle.cpp:562-614
+//                                      (+ BoundaryCondition::GetValueFromSameLevel = 0.0, BoundaryCondition.cpp:6-8)
+//   K5     k_restrict                 Rectangle::UpdateInterriorPoints                    Rectangle.cpp:314-337
+//   K4     k_ghost_coarse             Rectangle::UpdateDifferentLevelBoundaries           Rectangle.cpp:343-560
+//          k_corners                  Rectangle::UpdateCornerPoints                       Rectangle.cpp:1130-1214
+//   K6     k_level_boundary_fluxes    CalculateFluxToCoarse* / RGKGetFlux*                Rectangle.hpp:132-178, Rectangle.cpp:1032-1253
+//          k_boundary_c               Calculate{Same,Different}BoundaryC, UpdateSameBoundaryC   Rectangle.cpp:1625-1960
+//
+// One launch per level and pass; blockIdx.y selects the patch through the device patch table, threads run over the
+// strips / ghost cells / faces of the patch perimeter (work is proportional to perimeter, except the restriction and the
+// flagged-face scan which run over cells).  Compiled with -fmad=false: same operation order as the reference.
+//
+// Parallel execution is equivalent to the reference's serial patch loops because (i) same-level copies read neighbour
+// interiors only (patch positions and sizes on refined levels are multiples of r, checked by vrt_conn_derive), (ii) every
+// face of the limiter sync is written by at most two strips which compute the same value, (iii) levels are separate launches
+// in the reference's order.
+#include "vrt_internal.cuh"
+#include "vrt_device.cuh"
+#include <algorithm>
+#include <cmath>
+
+// ===================================================================================================================
+// host: connectivity
+// ===================================================================================================================
+namespace {
+
+inline bool on_line(int x, int y1, int y2) { return ((x - y1) > -1) && ((y2 - x) > -1); }
+inline long nsh(const vrt_patch_desc& q, int i, int j) { return (long)(q.n_p + 4) * (i + 2) + 2 + j; }
+
+// coarse patch `ic` learns which of its cells/faces the finer patch `jf` covers; `jf` learns its coarser neighbours
+void link_finer(vrt_conn& C, int ic, int jf) {
+    const int r = C.r;
+    const vrt_patch_desc &c = C.desc[ic], &f = C.desc[jf];
+    VrtConnPatch &cc = C.P[ic], &cf = C.P[jf];
+    const int fx0 = f.x_pos / r - c.x_pos, fp0 = f.p_pos / r - c.p_pos;      // finer patch in coarse-local cells
+    const int fnx = f.n_x / r, fnp = f.n_p / r;
+    const int fx1 = fx0 + fnx, fp1 = fp0 + fnp;
+    const int lo_x = std::max(0, fx0), hi_x = std::min(c.n_x, fx1);
+    const int lo_p = std::max(0, fp0), hi_p = std::min(c.n_p, fp1);
+    for (int i = lo_x; i < hi_x; i++)
+        for (int j = lo_p; j < hi_p; j++) { cc.flags[nsh(c, i, j)] |= VRT_NESTED; cc.finer[nsh(c, i, j)] = jf; }
+    const int last = cf.ns_x - 1;
+    auto corner_links = [&](int side) {
+        if (on_line(fp0 - 1, 0, c.n_p - 1)) { cf.nb[side][0] = ic; cf.same[side][0] = 0; }
+        if (on_line(fp1, 0, c.n_p - 1)) { cf.nb[side][last] = ic; cf.same[side][last] = 0; }
+    };
+    // upper x edge of the finer patch
+    if (fx1 < c.n_x + 1 && fx1 > -1)
+        for (int j = lo_p; j < hi_p; j++) { cc.finer_x[nsh(c, fx1, j)] = jf; cc.flags[nsh(c, fx1, j)] |= VRT_LBX; }
+    if (fx1 < c.n_x && fx1 > -1) {
+        for (int j = lo_p; j < hi_p; j++) { cf.nb[1][j - fp0 + 1] = ic; cf.same[1][j - fp0 + 1] = 0; }
+        corner_links(1);
+    }
+    // lower x edge
+    if (fx0 < c.n_x + 1 && fx0 > -1)
+        for (int j = lo_p; j < hi_p; j++) { cc.finer_x[nsh(c, fx0, j)] = jf; cc.flags[nsh(c, fx0, j)] |= VRT_LBX; }
+    if (fx0 < c.n_x + 1 && fx0 > 0) {
+        for (int j = lo_p; j < hi_p; j++) { cf.nb[0][j - fp0 + 1] = ic; cf.same[0][j - fp0 + 1] = 0; }
+        corner_links(0);
+    }
+    // upper / lower p edges
+    if (fp1 < c.n_p + 1 && fp1 > -1)
+        for (int i = lo_x; i < hi_x; i++) { cc.finer_p[nsh(c, i, fp1)] = jf; cc.flags[nsh(c, i, fp1)] |= VRT_LBP; }
+    if (fp1 < c.n_p && fp1 > -1)
+        for (int i = lo_x; i < hi_x; i++) { cf.nb[3][i - fx0] = ic; cf.same[3][i - fx0] = 0; }
+    if (fp0 < c.n_p + 1 && fp0 > -1)
+        for (int i = lo_x; i < hi_x; i++) { cc.finer_p[nsh(c, i, fp0)] = jf; cc.flags[nsh(c, i, fp0)] |= VRT_LBP; }
+    if (fp0 < c.n_p + 1 && fp0 > 0)
+        for (int i = lo_x; i < hi_x; i++) { cf.nb[2][i - fx0] = ic; cf.same[2][i - fx0] = 0; }
+}
+
+// patch `a` learns its same-level neighbour `b`
+void link_same(vrt_conn& C, int a, int b) {
+    const int r = C.r;
+    const vrt_patch_desc &A = C.desc[a], &B = C.desc[b];
+    VrtConnPatch& ca = C.P[a];
+    const int rx = B.x_pos - A.x_pos, rp = B.p_pos - A.p_pos, last = ca.ns_x - 1;
+    auto set = [&](int side, int e) { ca.nb[side][e] = b; ca.same[side][e] = 1; };
+    if (rx == A.n_x) {                                  // b right of a
+        if (on_line(-1, rp, rp + B.n_p - 1)) set(1, 0);
+        if (on_line(A.n_p, rp, rp + B.n_p - 1)) set(1, last);
+        for (int lo = std::max(B.p_pos, A.p_pos), hi = std::min(A.p_pos + A.n_p, B.p_pos + B.n_p); lo < hi; lo += r)
+            set(1, (lo - A.p_pos) / r + 1);
+    }
+    if (rx == -B.n_x) {                                 // b left of a
+        if (on_line(-1, rp, rp + B.n_p - 1)) set(0, 0);
+        if (on_line(A.n_p, rp, rp + B.n_p - 1)) set(0, last);
+        for (int lo = std::max(B.p_pos, A.p_pos), hi = std::min(A.p_pos + A.n_p, B.p_pos + B.n_p); lo < hi; lo += r)
+            set(0, (lo - A.p_pos) / r + 1);
+    }
+    if (rp == A.n_p) {                                  // b above a
+        if (on_line(-1, rx, rx + B.n_x - 1)) set(0, last);
+        if (on_line(A.n_x, rx, rx + B.n_x - 1)) set(1, last);
+        for (int lo = std::max(B.x_pos, A.x_pos), hi = std::min(A.x_pos + A.n_x, B.x_pos + B.n_x); lo < hi; lo += r)
+            set(3, (lo - A.x_pos) / r);
+    }
+    if (rp == -B.n_p) {                                 // b below a
+        if (on_line(-1, rx, rx + B.n_x - 1)) set(0, 0);
+        if (on_line(A.n_x, rx, rx + B.n_x - 1)) set(1, 0);
+        for (int lo = std::max(B.x_pos, A.x_pos), hi = std::min(A.x_pos + A.n_x, B.x_pos + B.n_x); lo < hi; lo += r)
+            set(2, (lo - A.x_pos) / r);
+    }
+}
+
+}  // namespace
+
+// Connectivity passes of Mesh::promoteHierarchyToMesh (Mesh.cpp:840-861): finer->coarser links for every (coarse, fine)
+// pair level by level, then same-level links; later links overwrite earlier ones, so patch order inside a level matters
+// and is the caller's (= Level::rectangles order).
+int vrt_conn_derive(vrt_conn& C, int n, const vrt_patch_desc* d, int r, int max_depth) {
+    C.r = r; C.max_depth = max_depth;
+    C.desc.assign(d, d + n);
+    C.P.assign(n, VrtConnPatch());
+    for (int p = 0; p < n; p++) {
+        const vrt_patch_desc& q = d[p];
+        if (q.depth < 0 || q.depth > max_depth || q.n_x < r || q.n_p < r || q.n_x % r || q.n_p % r) { C.err = "bad patch descriptor"; return VRT_ERR_ARG; }
+        if (q.depth < max_depth && (q.x_pos % r || q.p_pos % r)) { C.err = "patches on refined levels must start on a multiple of the refinement ratio"; return VRT_ERR_ARG; }
+        VrtConnPatch& cp = C.P[p];
+        cp.ns_x = q.n_p / r + 2; cp.ns_p = q.n_x / r;
+        const long npad = (long)(q.n_x + 4) * (q.n_p + 4);
+        for (int s = 0; s < 4; s++) { cp.nb[s].assign(s < 2 ? cp.ns_x : cp.ns_p, -1); cp.same[s].assign(s < 2 ? cp.ns_x : cp.ns_p, 1); }
+        cp.finer.assign(npad, -1); cp.finer_x.assign(npad, -1); cp.finer_p.assign(npad, -1);
+        cp.flags.assign(npad, 0);
+    }
+    std::vector<std::vector<int>> lv(max_depth + 1);
+    for (int p = 0; p < n; p++) lv[d[p].depth].push_back(p);
+    for (int l = 1; l <= max_depth; l++)
+        for (int a : lv[l]) for (int b : lv[l - 1]) link_finer(C, a, b);
+    for (int l = 0; l <= max_depth; l++)
+        for (int a : lv[l]) for (int b : lv[l]) if (a != b) link_same(C, a, b);
+    return 0;
+}
+
+extern "C" {
+int vrt_conn_create(vrt_conn** out, int n_patches, const vrt_patch_desc* patches, int refinement_ratio, int max_depth) {
+    if (!out || n_patches < 1 || !patches || refinement_ratio < 2 || max_depth < 0) return VRT_ERR_ARG;
+    vrt_conn* C = new vrt_conn();
+    int rc = vrt_conn_derive(*C, n_patches, patches, refinement_ratio, max_depth);
+    if (rc) { delete C; return rc; }
+    *out = C;
+    return 0;
+}
+int vrt_conn_strips(const vrt_conn* C, int patch, int side, int* nb, unsigned char* same) {
+    if (!C || patch < 0 || patch >= (int)C->P.size() || side < 0 || side > 3) return VRT_ERR_ARG;
+    const VrtConnPatch& p = C->P[patch];
+    const int ns = (int)p.nb[side].size();
+    for (int i = 0; i < ns; i++) { if (nb) nb[i] = p.nb[side][i]; if (same) same[i] = p.same[side][i]; }
+    return ns;
+}
+int vrt_conn_flags(const vrt_conn* C, int patch, unsigned char* flags) {
+    if (!C || patch < 0 || patch >= (int)C->P.size() || !flags) return VRT_ERR_ARG;
+    std::copy(C->P[patch].flags.begin(), C->P[patch].flags.end(), flags);
+    return 0;
+}
+void vrt_conn_destroy(vrt_conn* C) { delete C; }
+}
+
+// ===================================================================================================================
+// device
+// ===================================================================================================================
+namespace {
+
+// interpolationMatrix (Rectangle.cpp:76-89)
+__constant__ double c_IMr[12] = {0.104166666666667, -0.708333333333334, 0.708333333333334, -0.104166666666667,
+                                 0.117647058823529, 0.029411764705882,  0.029411764705882, 0.117647058823529,
+                                 -0.083333333333333, 0.166666666666667, -0.166666666666667, 0.083333333333334};
+
+__device__ __forceinline__ double* fstate(const VrtPatchDev& P, int val) { return val == 2 ? P.f2 : (val == 1 ? P.f1 : P.f0); }
+// Rectangle::GetValueFromSameLevel (Rectangle.cpp:307-312); nb < 0: BoundaryCondition -> 0.0
+__device__ __forceinline__ double same_level_value(const VrtPatchDev* all, int nb, int i, int j, int val) {
+    if (nb < 0) return 0.0;
+    const VrtPatchDev& Q = all[nb];
+    return fstate(Q, val)[NS(Q, i - Q.x_pos, j - Q.p_pos)];
+}
+// Rectangle::GetInterpolantsREF (Rectangle.cpp:121-137) with the coefficients of Rectangle.cpp:94-101 evaluated in place
+__device__ void interpolants_ref(int r, double f1, double f2, double f3, double f4, double f5, double* out) {
+    f5 -= f3; f4 -= f3; f2 -= f3; f1 -= f3;
+    double a1 = c_IMr[0] * f1 + c_IMr[1] * f2 + c_IMr[2] * f4 + c_IMr[3] * f5;
+    double a2 = c_IMr[4] * f1 + c_IMr[5] * f2 + c_IMr[6] * f4 + c_IMr[7] * f5;
+    double a3 = c_IMr[8] * f1 + c_IMr[9] * f2 + c_IMr[10] * f4 + c_IMr[11] * f5;
+    for (int i = 0; i < r; i++) {
+        double tl = -0.5 + i / (double)r, tr = -0.5 + (i + 1.0) / (double)r;
+        double c0 = (tl + tr) * 0.5;
+        double c1 = (tl * tl + tl * tr + tr * tr) / 3.0 - (1.0 / 12);
+        double c2 = (tl * tl * tl + tl * tl * tr + tl * tr * tr + tr * tr * tr) * 0.25;
+        out[i] = c0 * a1 + c1 * a2 + c2 * a3 + f3;
+    }
+}
+constexpr int RMAX = 4;   // largest refinement ratio the interpolation buffers are sized for
+// Rectangle::GetWenoValueFromCoarseLevel (Rectangle.cpp:343-415) on coarse patch Q; (i,j) are fine-level global cell
+// coordinates; out receives the two sub-cell layers nearest the fine patch (2r values) for d = 0..3
+__device__ void coarse_level_values(const VrtPatchDev& Q, int r, int i, int j, int d, int val, double* out) {
+    const double* f = fstate(Q, val);
+    const int ic = i / r - Q.x_pos, jc = j / r - Q.p_pos;
+    double temps[5][RMAX], ip[RMAX * RMAX], part[RMAX], sum = 0.0;
+    for (int k = -2; k < 3; k++)
+        interpolants_ref(r, f[NS(Q, ic - 2, jc + k)], f[NS(Q, ic - 1, jc + k)], f[NS(Q, ic, jc + k)], f[NS(Q, ic + 1, jc + k)], f[NS(Q, ic + 2, jc + k)], temps[k + 2]);
+    for (int k = 0; k < r; k++) {
+        interpolants_ref(r, temps[0][k], temps[1][k], temps[2][k], temps[3][k], temps[4][k], part);
+        for (int l = 0; l < r; l++) { ip[k * r + l] = part[l]; sum += part[l]; }
+    }
+    const double correction = f[NS(Q, ic, jc)] - 1.0 / (double)(r * r) * sum;
+    for (int k = 0; k < r * r; k++) ip[k] += correction;
+    if (d == 0) for (int k = 0; k < r; k++) { out[2 * k] = ip[r * k + r - 1]; out[2 * k + 1] = ip[r * k + r - 2]; }
+    else if (d == 1) for (int k = 0; k < r; k++) { out[2 * k] = ip[k]; out[2 * k + 1] = ip[r + k]; }
+    else if (d == 2) for (int k = 0; k < r; k++) { out[2 * k] = ip[r * k]; out[2 * k + 1] = ip[r * k + 1]; }
+    else for (int k = 0; k < r; k++) { out[2 * k] = ip[r * (r - 1) + k]; out[2 * k + 1] = ip[r * (r - 2) + k]; }
+}
+
+// ---- K3: same-level ghost copy, side strips only (corners belong to k_corners / k_ghost_coarse) ---------------------
+// thread t: [0, 2 n_p) cells of the xm / xp sides, [2 n_p, 2 n_p + 2 n_x) cells of the pm / pp sides; both ghost layers
+__global__ void k_ghost_same(const VrtPatchDev* level, const VrtPatchDev* all, int val, int r) {
+    const VrtPatchDev& P = level[blockIdx.y];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nx = P.n_x, np = P.n_p;
+    if (t >= 2 * np + 2 * nx) return;
+    double* f = fstate(P, val);
+    if (t < 2 * np) {
+        const int side = t / np, j = t % np, e = j / r + 1;
+        if (!P.same[side][e]) return;
+        const int nb = P.nb[side][e];
+        const int g1 = side == 0 ? -1 : nx, g2 = side == 0 ? -2 : nx + 1;
+        f[NS(P, g1, j)] = same_level_value(all, nb, P.x_pos + g1, P.p_pos + j, val);
+        f[NS(P, g2, j)] = same_level_value(all, nb, P.x_pos + g2, P.p_pos + j, val);
+    } else {
+        const int u = t - 2 * np, side = 2 + u / nx, i = u % nx, e = i / r;
+        if (!P.same[side][e]) return;
+        const int nb = P.nb[side][e];
+        const int g1 = side == 2 ? -1 : np, g2 = side == 2 ? -2 : np + 1;
+        f[NS(P, i, g1)] = same_level_value(all, nb, P.x_pos + i, P.p_pos + g1, val);
+        f[NS(P, i, g2)] = same_level_value(all, nb, P.x_pos + i, P.p_pos + g2, val);
+    }
+}
+
+// ---- K5: restriction of covered cells (Rectangle.cpp:314-337) -------------------------------------------------------
+__global__ void k_restrict(const VrtPatchDev* level, const VrtPatchDev* all, int val, int r) {
+    const VrtPatchDev& P = level[blockIdx.y];
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.npad) return;
+    if (!(P.flags[c] & VRT_NESTED)) return;
+    const int i = (int)(c / P.pitch) - 2, j = (int)(c % P.pitch) - 2;
+    const VrtPatchDev& Q = all[P.finer[c]];
+    const double* fq = fstate(Q, val);
+    const int i_f = (P.x_pos + i) * r - Q.x_pos, j_f = (P.p_pos + j) * r - Q.p_pos;
+    double t = 0.0;
+    for (int k = 0; k < r; k++) for (int l = 0; l < r; l++) t += fq[NS(Q, i_f + k, j_f + l)];
+    t /= (double)(r * r);     // std::pow((double)refinementRatio, 2.0) is exact
+    fstate(P, val)[c] = t;
+}
+
+// the four 2x2 ghost corners of a patch (Rectangle.cpp:1130-1214 = 484-560); c in [0, 8): side, which corner, p offset
+__device__ void corner_cell(const VrtPatchDev& P, const VrtPatchDev* all, int val, int r, int c) {
+    const int side = c >> 2, which = (c >> 1) & 1, jj = c & 1;
+    const int nx = P.n_x;
+    const int g1 = side == 0 ? -1 : nx, g2 = side == 0 ? -2 : nx + 1;
+    const int i = which == 0 ? -1 : P.ns_x - 2;                 // strip index: -1 below the patch, n_p/r above it
+    const int j = which == 0 ? r - 2 + jj : jj;                 // sub-cell inside the strip
+    const int e = i + 1;
+    const int nb = P.nb[side][e];
+    double* f = fstate(P, val);
+    if (!P.same[side][e]) {
+        double temp[2 * RMAX];
+        coarse_level_values(all[nb], r, P.x_pos + g1, P.p_pos + i * r, side == 0 ? 3 : 1, val, temp);
+        f[NS(P, g1, i * r + j)] = temp[2 * j];
+        f[NS(P, g2, i * r + j)] = temp[2 * j + 1];
+    } else {
+        f[NS(P, g1, i * r + j)] = same_level_value(all, nb, P.x_pos + g1, P.p_pos + i * r + j, val);
+        f[NS(P, g2, i * r + j)] = same_level_value(all, nb, P.x_pos + g2, P.p_pos + i * r + j, val);
+    }
+}
+__global__ void k_corners(const VrtPatchDev* level, const VrtPatchDev* all, int val, int r) {
+    if (threadIdx.x < 8) corner_cell(level[blockIdx.y], all, val, r, threadIdx.x);
+}
+
+// ---- K4: coarse -> fine ghost interpolation, one thread per strip with a coarser neighbour, then the corners ----------
+__global__ void k_ghost_coarse(const VrtPatchDev* level, const VrtPatchDev* all, int val, int r) {
+    const VrtPatchDev& P = level[blockIdx.y];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int sx = P.ns_x - 2, sp = P.ns_p;
+    if (t < 8) corner_cell(P, all, val, r, t);
+    const int u = t - 8;
+    if (u < 0 || u >= 2 * sx + 2 * sp) return;
+    int side, i;
+    if (u < 2 * sx) { side = u / sx; i = u % sx; } else { side = 2 + (u - 2 * sx) / sp; i = (u - 2 * sx) % sp; }
+    const int e = side < 2 ? i + 1 : i;
+    if (P.same[side][e]) return;
+    const VrtPatchDev& Q = all[P.nb[side][e]];
+    double* f = fstate(P, val);
+    double temp[2 * RMAX];
+    const int nx = P.n_x, np = P.n_p;
+    if (side == 0) {
+        coarse_level_values(Q, r, P.x_pos - 1, P.p_pos + i * r, 3, val, temp);
+        for (int j = 0; j < r; j++) { f[NS(P, -1, i * r + j)] = temp[2 * j]; f[NS(P, -2, i * r + j)] = temp[2 * j + 1]; }
+    } else if (side == 1) {
+        coarse_level_values(Q, r, P.x_pos + nx, P.p_pos + i * r, 1, val, temp);
+        for (int j = 0; j < r; j++) { f[NS(P, nx, i * r + j)] = temp[2 * j]; f[NS(P, nx + 1, i * r + j)] = temp[2 * j + 1]; }
+    } else if (side == 2) {
+        coarse_level_values(Q, r, P.x_pos + i * r, P.p_pos - 1, 0, val, temp);
+        for (int j = 0; j < r; j++) { f[NS(P, i * r + j, -1)] = temp[2 * j]; f[NS(P, i * r + j, -2)] = temp[2 * j + 1]; }
+    } else {
+        coarse_level_values(Q, r, P.x_pos + i * r, P.p_pos + np, 2, val, temp);
+        for (int j = 0; j < r; j++) { f[NS(P, i * r + j, np)] = temp[2 * j]; f[NS(P, i * r + j, np + 1)] = temp[2 * j + 1]; }
+    }
+}
+
+// ---- K6a: coarse-fine flux matching ------------------------------------------------------------------------------------
+// RGKGetFlux{X,P,XL,PL} (Rectangle.cpp:1032-1053, 1069-1098, 1216-1253) recomputed from the finer patch's f1;
+// kind 0 X, 1 P, 2 XL, 3 PL.  Recursion depth <= number of levels.
+__device__ double rgk_flux(const VrtPatchDev* all, int p, int i, int j, int kind, int r, const Sp& sp, const VrtFields& F);
+__device__ double flux_to_coarse(const VrtPatchDev* all, int p, int i, int j, int kind, int r, const Sp& sp, const VrtFields& F) {
+    const VrtPatchDev& P = all[p];
+    i = i * r - P.x_pos; j = j * r - P.p_pos;
+    double t = 0.0;
+    for (int k = 0; k < r; k++) t += (kind == 0 || kind == 2) ? rgk_flux(all, p, i, j + k, kind, r, sp, F) : rgk_flux(all, p, i + k, j, kind, r, sp, F);
+    t *= (1.0 / (double)(r * r));
+    return t;
+}
+__device__ double rgk_flux(const VrtPatchDev* all, int p, int i, int j, int kind, int r, const Sp& sp, const VrtFields& F) {
+    const VrtPatchDev& P = all[p];
+    const long idx = NS(P, i, j);
+    const bool isx = (kind == 0 || kind == 2);
+    if (P.flags[idx] & (isx ? VRT_LBX : VRT_LBP))
+        return flux_to_coarse(all, isx ? P.finer_x[idx] : P.finer_p[idx], P.x_pos + i, P.p_pos + j, kind, r, sp, F);
+    const double w3 = 1.0 / 48.0, dx_inv = 1 / P.dx, dp_inv = 1 / P.dp, q = sp.q, cc = VRT_CS * VRT_CS * sp.m;
+    const double* f = P.f1;
+    const double Kp = __dmul_rn(dp_inv, cc), Kx = __dmul_rn(cc, dx_inv);
+    if (isx) {
+        const double as = q * q * a_sq(F, finest_index(P, i));
+        const double g0 = gamma_(sp, momentum(P, sp, j), as), g1 = gamma_(sp, momentum(P, sp, j + 1), as);
+        const double am = __dmul_rn(Kp, __dadd_rn(g1, -g0));
+        if (kind == 2) return dx_inv * (am > 0.0 ? f[NS(P, i - 1, j)] : f[idx]) * am;
+        const double g2 = gamma_(sp, momentum(P, sp, j + 2.0), as), gm = gamma_(sp, momentum(P, sp, j - 1.0), as);
+        const double ap1 = __dmul_rn(Kp, __dadd_rn(g2, -g1)), am1 = __dmul_rn(Kp, __dadd_rn(g0, -gm));
+        const double fm = weno(f[NS(P, i - 2, j)], f[NS(P, i - 1, j)], f[idx], f[NS(P, i + 1, j)], am > 0.0);
+        const double fp1 = weno(f[NS(P, i - 2, j + 1)], f[NS(P, i - 1, j + 1)], f[idx + 1], f[NS(P, i + 1, j + 1)], ap1 > 0.0);
+        const double fm1 = weno(f[NS(P, i - 2, j - 1)], f[NS(P, i - 1, j - 1)], f[idx - 1], f[NS(P, i + 1, j - 1)], am1 > 0.0);
+        return dx_inv * (fm * am + w3 * (fp1 - fm1) * (ap1 - am1));
+    }
+    const double as_1 = q * q * a_sq(F, finest_index(P, i)), as_2 = q * q * a_sq(F, finest_index(P, i + 1));
+    const double Em = q * patch_efield(P, F, i), mom = momentum(P, sp, j);
+    const double G1 = gamma_(sp, mom, as_1), G2 = gamma_(sp, mom, as_2);
+    const double am = __dadd_rn(Em, -__dmul_rn(Kx, __dadd_rn(G2, -G1)));
+    if (kind == 3) return dp_inv * (am > 0.0 ? f[idx - 1] : f[idx]) * am;
+    const double as_0 = q * q * a_sq(F, finest_index(P, i - 1)), as_3 = q * q * a_sq(F, finest_index(P, i + 2));
+    const double Ep1 = q * patch_efield(P, F, i + 1), Em1 = q * patch_efield(P, F, i - 1);
+    const double G0 = gamma_(sp, mom, as_0), G3 = gamma_(sp, mom, as_3);
+    const double ap1 = __dadd_rn(Ep1, -__dmul_rn(Kx, __dadd_rn(G3, -G2)));
+    const double am1 = __dadd_rn(Em1, -__dmul_rn(Kx, __dadd_rn(G1, -G0)));
+    const long cp = idx + P.pitch, cm = idx - P.pitch;
+    const double fm = weno(f[idx - 2], f[idx - 1], f[idx], f[idx + 1], am > 0.0);
+    const double fp1 = weno(f[cp - 2], f[cp - 1], f[cp], f[cp + 1], ap1 > 0.0);
+    const double fm1 = weno(f[cm - 2], f[cm - 1], f[cm], f[cm + 1], am1 > 0.0);
+    return dp_inv * (fm * am + w3 * (fp1 - fm1) * (ap1 - am1));
+}
+// faces flagged is_interrior_level_boundary_{x,p}: flux := mean of the finer patch's face fluxes (Rectangle.cpp:1313-1394)
+__global__ void k_level_boundary_fluxes(const VrtPatchDev* level, const VrtPatchDev* all, int step, int r, Sp sp, VrtFields F) {
+    const VrtPatchDev& P = level[blockIdx.y];
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.npad) return;
+    const unsigned char fl = P.flags[c];
+    if (!(fl & (VRT_LBX | VRT_LBP))) return;
+    const int i = (int)(c / P.pitch) - 2, j = (int)(c % P.pitch) - 2;
+    const int nx = P.n_x, np = P.n_p;
+    if ((fl & VRT_LBX) && i >= 0 && i <= nx && j >= -1 && j <= np) {
+        P.FxH[step * P.npad + c] = flux_to_coarse(all, P.finer_x[c], P.x_pos + i, P.p_pos + j, 0, r, sp, F);
+        if (step == 0) P.FxL[c] = flux_to_coarse(all, P.finer_x[c], P.x_pos + i, P.p_pos + j, 2, r, sp, F);
+    }
+    if ((fl & VRT_LBP) && i >= -1 && i <= nx && j >= 0 && j <= np) {
+        P.FpH[step * P.npad + c] = flux_to_coarse(all, P.finer_p[c], P.x_pos + i, P.p_pos + j, 1, r, sp, F);
+        if (step == 0) P.FpL[c] = flux_to_coarse(all, P.finer_p[c], P.x_pos + i, P.p_pos + j, 3, r, sp, F);
+    }
+}
+
+// ---- K6b: limiter sync, one thread per side strip ------------------------------------------------------------------------
+// pass 4: CalculateSameBoundaryC -> SetCFromSameLevel (Rectangle.cpp:1835-1877, 1795-1833)
+// pass 5: CalculateDifferentBoundaryC -> SetCFromDifferentLevel (1706-1763, 1625-1704)
+// pass 6: UpdateSameBoundaryC -> UpdateCFromSameLevel (1919-1960, 1879-1917)
+__global__ void k_boundary_c(const VrtPatchDev* level, const VrtPatchDev* all, int pass, int r) {
+    const VrtPatchDev& Cl = level[blockIdx.y];       // the caller
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    const int sx = Cl.ns_x - 2, sp = Cl.ns_p;
+    if (u >= 2 * sx + 2 * sp) return;
+    int t, s;
+    if (u < 2 * sx) { t = u / sx; s = u % sx; } else { t = 2 + (u - 2 * sx) / sp; s = (u - 2 * sx) % sp; }
+    const int e = t < 2 ? s + 1 : s;
+    const bool same = Cl.same[t][e];
+    const int nb = Cl.nb[t][e];
+    if ((pass == 5) == same) return;
+    if (nb < 0) return;                            // BoundaryCondition: zero-trip loops (quirk Q8)
+    const VrtPatchDev& N = all[nb];
+    // global coordinates of the first face of the strip
+    const int gi = t == 1 ? Cl.x_pos + Cl.n_x : (t < 2 ? Cl.x_pos : Cl.x_pos + r * s);
+    const int gj = t == 3 ? Cl.p_pos + Cl.n_p : (t < 2 ? Cl.p_pos + r * s : Cl.p_pos);
+    const int icl = gi - Cl.x_pos, jcl = gj - Cl.p_pos;
+    const bool xdir = t < 2;
+    // cell of the caller adjacent to the face on the caller's side (t = 0, 2: the face's own cell; t = 1, 3: one below)
+    const int ax = (t == 1) ? -1 : 0, ap = (t == 3) ? -1 : 0;
+    if (pass == 5) {
+        const int ico = gi / r - N.x_pos, jco = gj / r - N.p_pos;
+        const long nc = NS(N, ico, jco);
+        double cv = xdir ? N.Cx[nc] : N.Cp[nc];
+        for (int k = 0; k < r; k++) {
+            const long fc = xdir ? NS(Cl, icl, jcl + k) : NS(Cl, icl + k, jcl);
+            const long ac = xdir ? NS(Cl, icl + ax, jcl + k) : NS(Cl, icl + k, jcl + ap);
+            const double fds = xdir ? Cl.FxDS[fc] : Cl.FpDS[fc];
+            // t = 0, 2: the fine cell receives a positive flux (Rp); t = 1, 3: it loses it (Rm)
+            const bool recv = (t == 0 || t == 2);
+            cv = fmin(cv, (fds > 0.0) == recv ? Cl.Rp[ac] : Cl.Rm[ac]);
+        }
+        {   // the coarse cell on the far side of the face
+            const long oc = (t == 0) ? NS(N, ico - 1, jco) : ((t == 2) ? NS(N, ico, jco - 1) : nc);
+            const double fds = xdir ? N.FxDS[nc] : N.FpDS[nc];
+            const bool recv = (t == 1 || t == 3);   // t = 1, 3: the coarse cell is the face's own cell
+            cv = fmin(cv, (fds > 0.0) == recv ? N.Rp[oc] : N.Rm[oc]);
+        }
+        for (int k = 0; k < r; k++) {
+            const long fc = xdir ? NS(Cl, icl, jcl + k) : NS(Cl, icl + k, jcl);
+            if (xdir) Cl.Cx[fc] = cv; else Cl.Cp[fc] = cv;
+        }
+        if (xdir) N.Cx[nc] = cv; else N.Cp[nc] = cv;
+        return;
+    }
+    const int in = gi - N.x_pos, jn = gj - N.p_pos;
+    for (int k = 0; k < r; k++) {
+        const long fn = xdir ? NS(N, in, jn + k) : NS(N, in + k, jn);        // the face in the neighbour
+        const long fc = xdir ? NS(Cl, icl, jcl + k) : NS(Cl, icl + k, jcl);  // the face in the caller
+        double cv;
+        if (pass == 4) {
+            // the two cells sharing the face: `lo` below it, `hi` above it; the caller holds `hi` for t = 0, 2
+            const long ac = xdir ? NS(Cl, icl + ax, jcl + k) : NS(Cl, icl + k, jcl + ap);
+            const long an = (t == 0) ? NS(N, in - 1, jn + k) : ((t == 2) ? NS(N, in + k, jn - 1) : fn);
+            const double fds = xdir ? N.FxDS[fn] : N.FpDS[fn];
+            const bool caller_hi = (t == 0 || t == 2);
+            const double Rp_hi = caller_hi ? Cl.Rp[ac] : N.Rp[an], Rm_hi = caller_hi ? Cl.Rm[ac] : N.Rm[an];
+            const double Rp_lo = caller_hi ? N.Rp[an] : Cl.Rp[ac], Rm_lo = caller_hi ? N.Rm[an] : Cl.Rm[ac];
+            cv = fds > 0.0 ? fmin(Rp_hi, Rm_lo) : fmin(Rp_lo, Rm_hi);
+        } else {
+            cv = xdir ? fmin(N.Cx[fn], Cl.Cx[fc]) : fmin(N.Cp[fn], Cl.Cp[fc]);
+        }
+        if (xdir) { N.Cx[fn] = cv; Cl.Cx[fc] = cv; } else { N.Cp[fn] = cv; Cl.Cp[fc] = cv; }
+    }
+}
+
+inline Sp make_sp(const VrtSpecies& s) { return Sp{s.m, s.q, s.pmin, 1 / s.m}; }
+
+}  // namespace
+
+// ===================================================================================================================
+// host launchers
+// ===================================================================================================================
+int vrt_amr_upload_connectivity(vrt_ctx* c, int s, const vrt_conn& C) {
+    VrtSpeciesState& S = c->S[s];
+    const int n = (int)C.P.size();
+    // pool layout per patch (table order): nb[4] ints, finer/finer_x/finer_p ints, then bytes same[4], flags
+    size_t bytes = 0;
+    std::vector<size_t> off(n);
+    for (int ti = 0; ti < n; ti++) {
+        const VrtConnPatch& p = C.P[S.table_order[ti]];
+        off[ti] = bytes;
+        size_t ints = 2 * (size_t)p.ns_x + 2 * (size_t)p.ns_p + 3 * p.flags.size();
+        size_t chars = 2 * (size_t)p.ns_x + 2 * (size_t)p.ns_p + p.flags.size();
+        bytes += ints * sizeof(int) + ((chars + 15) / 16) * 16;
+    }
+    std::vector<unsigned char> host(bytes, 0);
+    if (S.conn_pool) { cudaFree(S.conn_pool); S.conn_pool = nullptr; }
+    VRT_CUDA(c, cudaMalloc(&S.conn_pool, std::max<size_t>(bytes, 16)));
+    unsigned char* dbase = (unsigned char*)S.conn_pool;
+    S.has_amr = false;
+    for (int ti = 0; ti < n; ti++) {
+        const VrtConnPatch& p = C.P[S.table_order[ti]];
+        VrtPatchDev& T = S.table[ti];
+        T.ns_x = p.ns_x; T.ns_p = p.ns_p;
+        int* hi = (int*)(host.data() + off[ti]);
+        int* di = (int*)(dbase + off[ti]);
+        size_t k = 0;
+        auto to_table = [&](int caller_idx) { return caller_idx < 0 ? -1 : S.table_index[caller_idx]; };
+        for (int sd = 0; sd < 4; sd++) {
+            T.nb[sd] = di + k;
+            for (int v : p.nb[sd]) { hi[k++] = to_table(v); if (v >= 0) S.has_amr = true; }
+        }
+        const std::vector<int>* planes[3] = {&p.finer, &p.finer_x, &p.finer_p};
+        int** dst[3] = {&T.finer, &T.finer_x, &T.finer_p};
+        for (int q = 0; q < 3; q++) {
+            *dst[q] = di + k;
+            for (int v : *planes[q]) hi[k++] = to_table(v);
+        }
+        unsigned char* hc = (unsigned char*)(hi + k);
+        unsigned char* dc = (unsigned char*)(di + k);
+        size_t m = 0;
+        for (int sd = 0; sd < 4; sd++) {
+            T.same[sd] = dc + m;
+            for (unsigned char v : p.same[sd]) hc[m++] = v;
+        }
+        T.flags = dc + m;
+        for (unsigned char v : p.flags) { hc[m++] = v; if (v) S.has_amr = true; }
+    }
+    VRT_CUDA(c, cudaMemcpyAsync(S.conn_pool, host.data(), bytes, cudaMemcpyHostToDevice, c->stream));
+    VRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (size_t p = 0; p < S.patches.size(); p++) S.patches[p] = S.table[S.table_index[p]];
+    return 0;
+}
+
+static unsigned blocks(long n, int b = 128) { return (unsigned)((n + b - 1) / b); }
+
+// Mesh::PushData(val) (Mesh.cpp:91-106)
+int vrt_amr_push_data(vrt_ctx* c, int s, int val) {
+    VrtSpeciesState& S = c->S[s];
+    const int nl = (int)S.level_patches.size(), r = c->refinement_ratio;
+    const VrtPatchDev* all = S.d_patches;
+    auto perim = [&](int l) { long m = 0; for (int p : S.level_patches[l]) m = std::max<long>(m, 2L * S.table[p].n_x + 2L * S.table[p].n_p); return m; };
+    auto strips = [&](int l) { long m = 0; for (int p : S.level_patches[l]) m = std::max<long>(m, 2L * (S.table[p].ns_x - 2) + 2L * S.table[p].ns_p); return m; };
+    auto npadmax = [&](int l) { long m = 0; for (int p : S.level_patches[l]) m = std::max(m, S.table[p].npad); return m; };
+    auto same_pass = [&](int l) {
+        if (S.level_patches[l].empty()) return;
+        k_ghost_same<<<dim3(blocks(perim(l)), (unsigned)S.level_patches[l].size()), 128, 0, c->stream>>>(all + S.level_patches[l][0], all, val, r);
+        c->launches += 1;
+    };
+    same_pass(0);
+    for (int l = 1; l < nl; l++) {
+        if (!S.level_patches[l].empty() && !S.level_patches[l - 1].empty()) {
+            k_restrict<<<dim3(blocks(npadmax(l), 256), (unsigned)S.level_patches[l].size()), 256, 0, c->stream>>>(all + S.level_patches[l][0], all, val, r);
+            c->launches += 1;
+        }
+        same_pass(l);
+    }
+    if (!S.level_patches[nl - 1].empty()) {
+        k_corners<<<dim3(1, (unsigned)S.level_patches[nl - 1].size()), 32, 0, c->stream>>>(all + S.level_patches[nl - 1][0], all, val, r);
+        c->launches += 1;
+    }
+    for (int l = nl - 1; l > 0; l--) {
+        if (S.level_patches[l - 1].empty()) continue;
+        k_ghost_coarse<<<dim3(blocks(strips(l - 1) + 8), (unsigned)S.level_patches[l - 1].size()), 128, 0, c->stream>>>(all + S.level_patches[l - 1][0], all, val, r);
+        c->launches += 1;
+    }
+    VRT_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+// Mesh::PushBoundaryC (Mesh.cpp:904-917): passes 4, 5, 6 over all levels, finest first
+int vrt_amr_push_boundary_c(vrt_ctx* c, int s) {
+    VrtSpeciesState& S = c->S[s];
+    if (!S.has_amr) return 0;     // every strip faces the BoundaryCondition object: zero-trip loops (quirk Q8)
+    const int nl = (int)S.level_patches.size(), r = c->refinement_ratio;
+    const VrtPatchDev* all = S.d_patches;
+    for (int pass = 4; pass <= 6; pass++)
+        for (int l = 0; l < nl; l++) {
+            if (S.level_patches[l].empty()) continue;
+            long m = 0;
+            for (int p : S.level_patches[l]) m = std::max<long>(m, 2L * (S.table[p].ns_x - 2) + 2L * S.table[p].ns_p);
+            k_boundary_c<<<dim3(blocks(m), (unsigned)S.level_patches[l].size()), 128, 0, c->stream>>>(all + S.level_patches[l][0], all, pass, r);
+            c->launches += 1;
+        }
+    VRT_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+int vrt_amr_level_boundary_fluxes(vrt_ctx* c, int s, int depth, int step) {
+    VrtSpeciesState& S = c->S[s];
+    if (depth == 0 || S.level_patches[depth].empty() || S.level_patches[depth - 1].empty()) return 0;
+    long m = 0;
+    for (int p : S.level_patches[depth]) m = std::max(m, S.table[p].npad);
+    k_level_boundary_fluxes<<<dim3(blocks(m, 128), (unsigned)S.level_patches[depth].size()), 128, 0, c->stream>>>(
+        S.d_patches + S.level_patches[depth][0], S.d_patches, step, c->refinement_ratio, make_sp(S.sp), c->F);
+    c->launches += 1;
+    VRT_CUDA(c, cudaGetLastError());
+    return 0;
+}

@@ -21,7 +21,7 @@ __device__ __forceinline__ double a_sq(const VrtFields& F, int i) { return F.a_s
 __device__ __forceinline__ double patch_efield(const VrtPatchDev& P, const VrtFields& F, int i) {
     int j = finest_index(P, i);
     double t = 0.0;
-    for (int k = 0; k < P.rtb; k++) t += F.E[j + k + 2];
+    for (int k = 0; k < P.rtb; k++) t += F.E[j + k + F.epad];
     t *= (1.0 / (double)P.rtb);
     return t;
 }

@@ -185,7 +185,7 @@ __device__ __forceinline__ double efield_base(const VrtFields& F, int i) {
     const double fieldCoef = 1.0 / (12 * F.dx);
     return -fieldCoef * (8 * (F.PHI[ip1] - F.PHI[im1]) - F.PHI[ip2] + F.PHI[im2]);
 }
-// Ex0 += -(GetEfield(-1)+GetEfield(0))*0.5 (EMSolver.cpp:191, quirk Q4), then tabulate E on [-2, N+1]
+// Ex0 += -(GetEfield(-1)+GetEfield(0))*0.5 (EMSolver.cpp:191, quirk Q4), then tabulate E on [-epad, N+epad)
 __global__ void k_efield(VrtFields F, int update_ex0) {
     __shared__ double ex0_new;
     if (threadIdx.x == 0) {
@@ -194,8 +194,8 @@ __global__ void k_efield(VrtFields F, int update_ex0) {
         ex0_new = ex0;
     }
     __syncthreads();
-    int i = blockIdx.x * blockDim.x + threadIdx.x - 2;
-    if (i <= F.N + 1) F.E[i + 2] = efield_base(F, i) + ex0_new;
+    int i = blockIdx.x * blockDim.x + threadIdx.x - F.epad;
+    if (i < F.N + F.epad) F.E[i + F.epad] = efield_base(F, i) + ex0_new;
     if (blockIdx.x == 0 && threadIdx.x == 0) F.Ex0[1] = ex0_new;   // staged; committed by k_commit_ex0
 }
 __global__ void k_commit_ex0(VrtFields F) { F.Ex0[0] = F.Ex0[1]; }
@@ -209,7 +209,7 @@ __global__ void k_cfl(VrtFields F, CflSpecies sp) {
         double Azv = F.Y[VRT_AZ][i], Ayv = F.Y[VRT_AY][i];
         double As = Ayv * Ayv + Azv * Azv, t = 0.0;
         for (int j = 0; j < sp.n; j++) t = fmax(t, fabs(sp.q[j]) / sp.m[j] / sqrt(1 + As / ((sp.m[j] * VRT_CS) * (sp.m[j] * VRT_CS))) * sp.dps[j]);
-        pc = fmax(pc, t * fabs(Ayv * F.Y[VRT_BZ][i] - Azv * F.Y[VRT_BY][i]) + sp.dpsMax * fabs(F.E[i + 2]));
+        pc = fmax(pc, t * fabs(Ayv * F.Y[VRT_BZ][i] - Azv * F.Y[VRT_BY][i]) + sp.dpsMax * fabs(F.E[i + F.epad]));
     }
     for (int o = 16; o > 0; o >>= 1) pc = fmax(pc, __shfl_down_sync(0xffffffffu, pc, o));
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = pc;
@@ -269,7 +269,7 @@ int vrt_fields_rhs_update_faces(vrt_ctx* c, int step, const VrtStepParams* d_par
 int vrt_fields_poisson(vrt_ctx* c) {
     VrtFields& F = c->F;
     k_poisson<<<1, PT, 0, c->stream>>>(F);
-    k_efield<<<grid1(F.N + 4), 256, 0, c->stream>>>(F, 1);
+    k_efield<<<grid1(F.N + 2 * F.epad), 256, 0, c->stream>>>(F, 1);
     k_commit_ex0<<<1, 1, 0, c->stream>>>(F);
     c->launches += 3;
     VRT_CUDA(c, cudaGetLastError());
@@ -279,7 +279,7 @@ int vrt_fields_poisson(vrt_ctx* c) {
 // recompute the E table from the current PHI and Ex0 (after uploads)
 int vrt_fields_refresh_efield(vrt_ctx* c) {
     VrtFields& F = c->F;
-    k_efield<<<grid1(F.N + 4), 256, 0, c->stream>>>(F, 0);
+    k_efield<<<grid1(F.N + 2 * F.epad), 256, 0, c->stream>>>(F, 0);
     c->launches += 1;
     VRT_CUDA(c, cudaGetLastError());
     return 0;
@@ -317,6 +317,25 @@ int vrt_fields_assemble_add(vrt_ctx* c, int s, const double* chargeR, const doub
     VRT_CUDA(c, cudaGetLastError());
     return 0;
 }
+// Level::CollectRhoAndJ (Level.cpp:42-62): chargeL / currentL live in the first 2N doubles of the Poisson workspace
+int vrt_fields_level_begin(vrt_ctx* c) {
+    k_zero2<<<grid1(c->F.N), 256, 0, c->stream>>>(c->F.scratch, c->F.scratch + c->F.N, c->F.N);
+    c->launches += 1;
+    VRT_CUDA(c, cudaGetLastError());
+    return 0;
+}
+int vrt_fields_level_accumulate(vrt_ctx* c, const double* chargeR, const double* currentR, int x0, int n) {
+    k_add_moments<<<grid1(n), 256, 0, c->stream>>>(c->F.scratch, c->F.scratch + c->F.N, chargeR, currentR, x0, n);
+    c->launches += 1;
+    VRT_CUDA(c, cudaGetLastError());
+    return 0;
+}
+int vrt_fields_level_add(vrt_ctx* c, int s) {
+    k_add_moments<<<grid1(c->F.N), 256, 0, c->stream>>>(c->S[s].d_charges, c->F.J, c->F.scratch, c->F.scratch + c->F.N, 0, c->F.N);
+    c->launches += 1;
+    VRT_CUDA(c, cudaGetLastError());
+    return 0;
+}
 int vrt_fields_assemble_end(vrt_ctx* c) {
     for (int s = 0; s < c->n_species; s++) {
         k_add1<<<grid1(c->F.N), 256, 0, c->stream>>>(c->F.charge, c->S[s].d_charges, c->F.N);
@@ -328,7 +347,7 @@ int vrt_fields_assemble_end(vrt_ctx* c) {
 int vrt_fields_snapshot_stage0(vrt_ctx* c) {
     VrtFields& F = c->F;
     k_copy<<<grid1(F.N + 1), 256, 0, c->stream>>>(F.a_squared0, F.a_squared, F.N + 1);
-    k_copy<<<grid1(F.N + 4), 256, 0, c->stream>>>(F.E0, F.E, F.N + 4);
+    k_copy<<<grid1(F.N + 2 * F.epad), 256, 0, c->stream>>>(F.E0, F.E, F.N + 2 * F.epad);
     c->launches += 2;
     VRT_CUDA(c, cudaGetLastError());
     return 0;

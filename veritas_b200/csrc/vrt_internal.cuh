@@ -36,7 +36,8 @@ struct VrtFields {
     double* a_squared;          // N+1 (x-faces; entry N never written, quirk Q2)
     double* a_squared0;         // stage-0 snapshot (fused path: low-order flux recompute, quirk Q1)
     double* PHI;                // N
-    double* E;                  // N+4: E[i+2] = EMFieldSolver::GetEfield(i), i in [-2, N+1]
+    int epad;                   // E is tabulated on [-epad, N+epad): epad = max(2, r^max_depth) (coarse ghost columns average rtb cells)
+    double* E;                  // N+2*epad: E[i+epad] = EMFieldSolver::GetEfield(i)
     double* E0;                 // stage-0 snapshot of E
     double* charge; double* J; double* neutral;   // N each
     double* Ex0;                // device scalar
@@ -60,7 +61,31 @@ struct VrtPatchDev {
     double *FxL, *FpL;           // slot 0 (quirk Q1)
     double *FxLS, *FpLS, *FxDS, *FpDS, *Rp, *Rm, *Cx, *Cp;
     double *chargeR, *currentR;  // n_x*rtb each
+    // AMR connectivity (vrt_amr.cu), derived from the patch descriptors as Rectangle::CalculateConnectivitySame /
+    // CalculateConnectivityFromFiner do (Rectangle.cpp:671-864).  Neighbour indices are device-table indices, -1 = the
+    // BoundaryCondition object.  Side 0 xm, 1 xp (n_p/r + 2 strips incl. the two corners), 2 pm, 3 pp (n_x/r strips).
+    int ns_x, ns_p;
+    int* nb[4]; unsigned char* same[4];
+    int *finer, *finer_x, *finer_p;   // per padded cell: finer patch covering the cell / owning the flagged x- or p-face
+    unsigned char* flags;             // VRT_NESTED | VRT_LBX | VRT_LBP per padded cell
 };
+enum { VRT_NESTED = 1, VRT_LBX = 2, VRT_LBP = 4 };
+
+// Host-side connectivity tables of one species' hierarchy (caller's patch numbering unless noted)
+struct VrtConnPatch {
+    int ns_x = 0, ns_p = 0;
+    std::vector<int> nb[4];
+    std::vector<unsigned char> same[4];
+    std::vector<int> finer, finer_x, finer_p;
+    std::vector<unsigned char> flags;
+};
+struct vrt_conn {
+    int r = 2, max_depth = 0;
+    std::vector<vrt_patch_desc> desc;
+    std::vector<VrtConnPatch> P;
+    std::string err;
+};
+int vrt_conn_derive(vrt_conn& C, int n, const vrt_patch_desc* d, int r, int max_depth);
 
 // Fused-path storage of one full-domain (or x-slab) single-level patch: three rotating f planes and five
 // stored high-order flux pairs.  Rows are x columns (slow), p is contiguous.  GX ghost columns per side.
@@ -87,8 +112,11 @@ struct VrtSpeciesState {
     std::vector<VrtPatchDev> patches;    // host copy of the descriptors (device pointers inside), caller's numbering
     std::vector<VrtPatchDev> table;      // the same, grouped by depth = order of the device table
     std::vector<int> table_index;        // caller's patch number -> table index
+    std::vector<int> table_order;        // table index -> caller's patch number
     VrtPatchDev* d_patches = nullptr;    // device copy of `table`
     std::vector<double*> allocations;
+    void* conn_pool = nullptr;           // device pool holding the connectivity tables of all patches
+    bool has_amr = false;                // any nested cell / coarse-fine face / same-level neighbour
     std::vector<std::vector<int>> level_patches;   // table indices per depth (contiguous ranges)
     // fused path
     VrtSlabDev slab;
@@ -134,8 +162,12 @@ struct vrt_ctx {
 // ---- launchers implemented in the kernel translation units -----------------------------------------
 // split path (vrt_split.cu, compiled with -fmad=false)
 int vrt_split_substep(vrt_ctx* c, int s, int depth, const double* d_dt, int step, int substep);
-int vrt_split_fill_domain_ghosts(vrt_ctx* c, int s, int depth, int val);
 int vrt_split_moments(vrt_ctx* c, int s);
+// AMR kernels (vrt_amr.cu, compiled with -fmad=false)
+int vrt_amr_upload_connectivity(vrt_ctx* c, int s, const vrt_conn& C);
+int vrt_amr_push_data(vrt_ctx* c, int s, int val);
+int vrt_amr_push_boundary_c(vrt_ctx* c, int s);
+int vrt_amr_level_boundary_fluxes(vrt_ctx* c, int s, int depth, int step);
 // 1-D solver (vrt_fields.cu, compiled with -fmad=false)
 int vrt_fields_rhs_update_faces(vrt_ctx* c, int step, const VrtStepParams* d_params);
 int vrt_fields_poisson(vrt_ctx* c);

@@ -42,26 +42,31 @@ __global__ void k_speeds_faces(const VrtPatchDev* patches, Sp sp, VrtFields F) {
     }
 }
 
-// sub-step 0, part 2: high/low-order fluxes and the RK combination over the whole padded array
-// (Rectangle.cpp:1313-1517).  FxL/FpL hold slot 0 only (quirk Q1).
-__global__ void k_fluxes(const VrtPatchDev* patches, int step, const double* d_dt) {
+// sub-step 0, part 2: high/low-order fluxes at faces not flagged as interior level boundaries (Rectangle.cpp:1313-1394;
+// flagged faces are filled by k_level_boundary_fluxes of vrt_amr.cu).  FxL/FpL hold slot 0 only (quirk Q1).
+__global__ void k_fluxes(const VrtPatchDev* patches, int step) {
     PATCH_THREAD_SETUP
     const double w3 = 1 / 48.0, dx_inv = 1 / P.dx, dp_inv = 1 / P.dp;
-    const double timestep = *d_dt;
+    const unsigned char fl = P.flags[c];
     double* FxHs = P.FxH + step * P.npad; double* FpHs = P.FpH + step * P.npad;
-    if (i >= 0 && i <= nx && j >= -1 && j <= np) {
+    if (i >= 0 && i <= nx && j >= -1 && j <= np && !(fl & VRT_LBX)) {
         double am = P.ex[c], ap1 = P.ex[c + 1], am1 = P.ex[c - 1];
         double fm = P.fx[c], fp1 = P.fx[c + 1], fm1 = P.fx[c - 1];
         FxHs[c] = dx_inv * (fm * am + w3 * (fp1 - fm1) * (ap1 - am1));
         if (step == 0) P.FxL[c] = dx_inv * ((am > 0.0 ? P.f1[NS(P, i - 1, j)] : P.f1[c]) * am);
     }
-    if (i >= -1 && i <= nx && j >= 0 && j <= np) {
+    if (i >= -1 && i <= nx && j >= 0 && j <= np && !(fl & VRT_LBP)) {
         long cp = c + P.pitch, cm = c - P.pitch;
         double am = P.ep[c], ap1 = P.ep[cp], am1 = P.ep[cm];
         double fm = P.fp[c], fp1 = P.fp[cp], fm1 = P.fp[cm];
         FpHs[c] = dp_inv * (fm * am + w3 * (fp1 - fm1) * (ap1 - am1));
         if (step == 0) P.FpL[c] = dp_inv * ((am > 0.0 ? P.f1[c - 1] : P.f1[c]) * am);
     }
+}
+// sub-step 0, part 3: RK combination over the whole padded array (Rectangle.cpp:1396-1517)
+__global__ void k_rk_combine(const VrtPatchDev* patches, int step, const double* d_dt) {
+    PATCH_THREAD_SETUP
+    const double timestep = *d_dt;
     double a[6], aSum = 0.0;
     for (int k = 0; k <= step; k++) { a[k] = c_tabs.a[step][k] * timestep; aSum = (k == 0) ? a[0] : aSum + a[k]; }
     double xl = aSum * P.FxL[c], pl = aSum * P.FpL[c];
@@ -129,15 +134,6 @@ __global__ void k_commit(const VrtPatchDev* patches) {
     PATCH_THREAD_SETUP
     P.f0[c] = P.f1[c];
 }
-// Ghost fill when every neighbour is the physical boundary: BoundaryCondition::GetValueFromSameLevel == 0.0
-// (BoundaryCondition.cpp:6-8) through UpdateSameLevelBoundaries + UpdateCornerPoints (Rectangle.cpp:562-614, 1130-1214)
-__global__ void k_zero_ghosts(const VrtPatchDev* patches, int val) {
-    PATCH_THREAD_SETUP
-    if (i >= 0 && i < nx && j >= 0 && j < np) return;
-    double* f = val == 2 ? P.f2 : (val == 1 ? P.f1 : P.f0);
-    f[c] = 0.0;
-}
-
 // ---- moments: Rectangle::CalculateRhoAndJ, USINGMKL branch (Rectangle.cpp:157-282) -------------------------
 __constant__ double c_IM[12] = {0.104166666666667, -0.708333333333334, 0.708333333333334, -0.104166666666667,
                                 0.117647058823529, 0.029411764705882,  0.029411764705882, 0.117647058823529,
@@ -179,6 +175,7 @@ __global__ void __launch_bounds__(128) k_moments(const VrtPatchDev* patches, Sp 
     const double a2 = q * q * cell_a_sq(F, (i + P.x_pos) * rtb + k);
     double rho = 0.0, cur = 0.0;
     for (int j = threadIdx.x; j < P.n_p; j += blockDim.x) {
+        if (P.flags[NS(P, i, j)] & VRT_NESTED) continue;   // cells covered by a finer patch (Rectangle.cpp:207-208)
         double t0 = rel_value(P, i, j, k), tm1 = rel_value(P, i, j - 1, k), tp1 = rel_value(P, i, j + 1, k);
         double pm1 = momentum(P, sp, j - 1), p0 = momentum(P, sp, j), p1 = momentum(P, sp, j + 1), p2 = momentum(P, sp, j + 2);
         double um1 = gamma_(sp, pm1, a2) + c1 * pm1, u0 = gamma_(sp, p0, a2) + c1 * p0;
@@ -225,9 +222,12 @@ int vrt_split_substep(vrt_ctx* c, int s, int depth, const double* d_dt, int step
     Sp sp = make_sp(S.sp);
     if (substep == 0) {
         k_speeds_faces<<<grid, 256, 0, c->stream>>>(tab, sp, c->F);
-        k_fluxes<<<grid, 256, 0, c->stream>>>(tab, step, d_dt);
+        k_fluxes<<<grid, 256, 0, c->stream>>>(tab, step);
+        c->launches += 2;
+        if (int r = vrt_amr_level_boundary_fluxes(c, s, depth, step)) return r;
+        k_rk_combine<<<grid, 256, 0, c->stream>>>(tab, step, d_dt);
         k_apply<<<grid, 256, 0, c->stream>>>(tab, 0);
-        c->launches += 3;
+        c->launches += 2;
     } else if (substep == 1) {
         k_limiter_r<<<grid, 256, 0, c->stream>>>(tab);
         k_limiter_c<<<grid, 256, 0, c->stream>>>(tab);
@@ -246,16 +246,11 @@ int vrt_split_substep(vrt_ctx* c, int s, int depth, const double* d_dt, int step
     return 0;
 }
 
-int vrt_split_fill_domain_ghosts(vrt_ctx* c, int s, int depth, int val) {
-    VrtSpeciesState& S = c->S[s];
-    dim3 grid; int first;
-    if (!level_grid(S, depth, &grid, &first)) return 0;
-    k_zero_ghosts<<<grid, 256, 0, c->stream>>>(S.d_patches + first, val);
-    c->launches += 1;
-    VRT_CUDA(c, cudaGetLastError());
-    return 0;
-}
-
+// Mesh::InterpolateRhoAndJToFinestMesh (Mesh.cpp:52-56): per level, patch moments are summed into a level array
+// (Level::CollectRhoAndJ, Level.cpp:42-62) which is then added to the species charge and the total current
+int vrt_fields_level_add(vrt_ctx* c, int s);
+int vrt_fields_level_begin(vrt_ctx* c);
+int vrt_fields_level_accumulate(vrt_ctx* c, const double* chargeR, const double* currentR, int x0, int n);
 int vrt_split_moments(vrt_ctx* c, int s) {
     VrtSpeciesState& S = c->S[s];
     Sp sp = make_sp(S.sp);
@@ -266,10 +261,12 @@ int vrt_split_moments(vrt_ctx* c, int s) {
         k_moments<<<dim3(mx, (unsigned)S.level_patches[d].size()), 128, 0, c->stream>>>(S.d_patches + first, sp, c->F);
         c->launches += 1;
         VRT_CUDA(c, cudaGetLastError());
+        if (int r = vrt_fields_level_begin(c)) return r;
         for (int p : S.level_patches[d]) {
             const VrtPatchDev& P = S.table[p];
-            if (int r = vrt_fields_assemble_add(c, s, P.chargeR, P.currentR, P.x_pos * P.rtb, P.n_x * P.rtb)) return r;
+            if (int r = vrt_fields_level_accumulate(c, P.chargeR, P.currentR, P.x_pos * P.rtb, P.n_x * P.rtb)) return r;
         }
+        if (int r = vrt_fields_level_add(c, s)) return r;
     }
     return 0;
 }

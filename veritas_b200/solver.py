@@ -13,6 +13,8 @@ CHARGES0 = 16
 EX0, TIME = 0, 1
 PATH_AUTO, PATH_SPLIT, PATH_FUSED = 0, 1, 2
 FIELD_NAMES = ("By", "Bz", "Ey", "Ez", "Ay", "Az")
+PLANES = ("FxH", "FpH", "FxL", "FpL", "FxDS", "FpDS", "Rp", "Rm", "Cx", "Cp", "ex", "ep", "fx", "fp")
+DESC_KEYS = ("depth", "x_pos", "p_pos", "n_x", "n_p", "up", "down", "left", "right")
 
 M_E = 9.10938291e-31      # veritas.cpp:16
 Q_E = 1.60217657e-19      # veritas.cpp:17
@@ -63,6 +65,7 @@ class Context:
         self.call("vrt_set_species", s, m, q, pmin, dp)
 
     def set_hierarchy(self, s, patches):
+        patches = [{k: p[k] for k in DESC_KEYS} for p in patches]
         arr = (PatchDesc * len(patches))(*[PatchDesc(**p) for p in patches])
         self.call("vrt_set_hierarchy", s, len(patches), arr)
         self.patches[s] = patches
@@ -85,6 +88,13 @@ class Context:
         if out is None:
             out = np.zeros((p["n_x"] + 4, p["n_p"] + 4))
         self.call("vrt_patch_download_f", s, patch, state, _p(out))
+        return out
+
+    def download_plane(self, s, patch, which, slot=0):
+        """One work plane (PLANES index) of a patch, padded layout; split path only."""
+        p = self.patches[s][patch]
+        out = np.zeros((p["n_x"] + 4, p["n_p"] + 4))
+        self.call("vrt_patch_download_plane", s, patch, which, slot, _p(out))
         return out
 
     def upload_field(self, which, slot, arr):
@@ -139,8 +149,9 @@ class Context:
     def last_step_launches(self):
         return self.L.vrt_last_step_launches(self.h)
 
-    def load_reference_state(self, dump, tag):
-        """Restart from an oracle/ref_harness dump (SURVEY.md H0 protocol P1): f per patch, the six transverse
+    def load_reference_state(self, dump, tag, keys=None):
+        """keys[s][patch] = record key of each patch (AMR hierarchies, oracle.port.hierarchy_from_dump).
+        Restart from an oracle/ref_harness dump (SURVEY.md H0 protocol P1): f per patch, the six transverse
         arrays (all slots), PHI, Ex0, neutralizationCharge, charge, J, a_squared, time."""
         for w, k in enumerate(FIELD_NAMES):
             a = dump[f"{tag}/{k}"]
@@ -155,7 +166,7 @@ class Context:
         self.set_scalar(TIME, float(dump[f"{tag}/time"][0]))
         for s in range(self.n_species):
             for r, _ in enumerate(self.patches[s]):
-                base = f"{tag}/s{s}/l0/r{r}/"
+                base = f"{tag}/" + (keys[s][r] if keys else f"s{s}/l0/r{r}") + "/"
                 if base + "f" in dump:
                     f0, f1 = dump[base + "f"][:, :, 0], dump[base + "f"][:, :, 1]
                 else:
@@ -197,9 +208,9 @@ class LaserPlasmaRun:
         for s in range(2):
             self.ctx.set_species(s, self.m[s], self.q[s], cd.pmin[s], cd.dp[s])
         if slab is not None:
+            from .parallel import slab_bounds
             rank, n_ranks = slab
-            n_loc = nx // n_ranks
-            self.ctx.call("vrt_set_slab", rank, n_ranks, rank * n_loc, (rank + 1) * n_loc)
+            self.ctx.call("vrt_set_slab", rank, n_ranks, *slab_bounds(nx, rank, n_ranks))
         self.ctx.set_path(path)
         self.ctx.call("vrt_set_option", 0, 1 if graph else 0)
         for s in range(2):
@@ -248,3 +259,28 @@ class LaserPlasmaRun:
 
     def cells(self):
         return self.nx * (self.np[0] + self.np[1])
+
+
+def connectivity(patches, r=2, max_depth=0):
+    """Host-side connectivity tables of a hierarchy (vrt_conn_*; needs no device): list per patch of
+    dict(nb=[4 lists], same=[4 lists], flags=uint8 array)."""
+    L = load()
+    patches = [{k: p[k] for k in DESC_KEYS} for p in patches]
+    arr = (PatchDesc * len(patches))(*[PatchDesc(**p) for p in patches])
+    h = C.c_void_p()
+    rc = L.vrt_conn_create(C.byref(h), len(patches), arr, r, max_depth)
+    if rc:
+        raise VrtError(f"vrt_conn_create failed ({rc})")
+    out = []
+    for k, p in enumerate(patches):
+        nb, same = [], []
+        for side in range(4):
+            n = (p["n_p"] // r + 2) if side < 2 else p["n_x"] // r
+            a = (C.c_int * n)(); b = (C.c_ubyte * n)()
+            assert L.vrt_conn_strips(h, k, side, a, b) == n
+            nb.append(list(a)); same.append(list(b))
+        fl = np.zeros((p["n_x"] + 4, p["n_p"] + 4), dtype=np.uint8)
+        assert L.vrt_conn_flags(h, k, fl.ctypes.data_as(C.POINTER(C.c_ubyte))) == 0
+        out.append(dict(nb=nb, same=same, flags=fl))
+    L.vrt_conn_destroy(h)
+    return out
