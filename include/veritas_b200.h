@@ -88,6 +88,9 @@ int vrt_get_scalar(vrt_ctx* ctx, int which, double* v);
 /* EMFieldSolver::AssembleRhoAndJ (EMSolver.cpp:104-122) -> Mesh::InterpolateRhoAndJToFinestMesh (Mesh.cpp:52-56)
  * -> Level::CollectRhoAndJ (Level.cpp:42-62) -> Rectangle::CalculateRhoAndJ (Rectangle.cpp:157-282). */
 int vrt_moments(vrt_ctx* ctx);
+/* Mesh::InterpolateRhoAndJToFinestMesh(charge, J) (Mesh.cpp:52-56) for species s: ADDS the species' charge and current on the finest
+ * grid to the two host arrays (x_size_finest doubles each). */
+int vrt_moments_species(vrt_ctx* ctx, int s, double* charge_host, double* j_host);
 /* EMFieldSolver::EnforceChargeNeutralization (EMSolver.cpp:621-629). */
 int vrt_enforce_neutralization(vrt_ctx* ctx);
 /* EMFieldSolver::UpdatePotential (EMSolver.cpp:156-192): periodic 4th-order Poisson + Ex0 update.  The
@@ -100,6 +103,9 @@ int vrt_vlasov_substep(vrt_ctx* ctx, int s, int depth, double dt, int step, int 
 /* Mesh::PushData(val) (Mesh.cpp:91-106) and Mesh::PushBoundaryC() (Mesh.cpp:904-917). */
 int vrt_push_data(vrt_ctx* ctx, int s, int val);
 int vrt_push_boundary_c(vrt_ctx* ctx, int s);
+/* Level::PushData(updateType, val) (Level.cpp:88-126) on the level of the given depth: 0 UpdateInterriorPoints, 1 UpdateSameLevelBoundaries,
+ * 2 UpdateDifferentLevelBoundaries, 3 UpdateCornerPoints, 4 CalculateSameBoundaryC, 5 CalculateDifferentBoundaryC, 6 UpdateSameBoundaryC. */
+int vrt_level_push(vrt_ctx* ctx, int s, int depth, int update_type, int val);
 /* EMFieldSolver::RGKStep(step, dt) (EMSolver.cpp:194-202) = RGKCalculateRHS + RGKUpdateIntermediateSolution +
  * InterpolateToFaces; by0/bz0 are the host-evaluated Settings::GetBY/GetBZ(0, time) (EMSolver.cpp:501-502). */
 int vrt_field_stage(vrt_ctx* ctx, int step, double dt, double by0, double bz0);

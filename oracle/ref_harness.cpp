@@ -10,6 +10,9 @@
 // laser-plasma case from veritas_b200/host/laser_plasma_case.hpp.  Private members of
 // SolverManager / EMFieldSolver / Rectangle are read with g++ -fno-access-control.
 //
+// The same source also compiles against the veritas_b200 host classes (veritas_b200/host/, -DVRT_HOST_BUILD): that build
+// (oracle/_ref/host_harness) is the drop-in test of the host layer — same case file, same dumps, GPU numerics.
+//
 // usage: ref_harness out.bin nx np Lfinest density steps [key=value ...]
 //   keys: dump_every=1 stage_dumps=0 regrid_every=0 threads=N refine_mode=0 tail_p0=2 pre_steps=-1
 //         time_only=0 internals=0 a0=1
@@ -62,6 +65,9 @@ static void put(const std::string& name, const double* data, std::initializer_li
 static void put1(const std::string& name, double v) { put(name, &v, {1}); }
 
 static void dump_state(SolverManager& SM, Settings& st, const std::string& tag, bool internals) {
+#ifdef VRT_HOST_BUILD
+    SM.SyncHost();     // veritas_b200 host classes: Rectangle::f and the EMFieldSolver arrays are mirrors of device data
+#endif
     EMFieldSolver& em = *SM.EMSolver;
     long M = em.x_size + em.n_prepad + em.n_postpad, N = em.x_size;
     put1(tag + "/time", st.time);
@@ -86,6 +92,7 @@ static void dump_state(SolverManager& SM, Settings& st, const std::string& tag, 
                                    (double)R.up, (double)R.down, (double)R.left, (double)R.right, R.relativeToBottom};
                 put(p + "/desc", desc, {10});
                 put(p + "/f", R.f.data(), {R.n_x + 4, R.n_p + 4, 3});
+#ifndef VRT_HOST_BUILD
                 if (internals) {
                     put(p + "/FxH", R.FxH.data(), {R.n_x + 4, R.n_p + 4, 6});
                     put(p + "/FpH", R.FpH.data(), {R.n_x + 4, R.n_p + 4, 6});
@@ -100,6 +107,7 @@ static void dump_state(SolverManager& SM, Settings& st, const std::string& tag, 
                     put(p + "/ex", R.ex.data(), {R.n_x + 4, R.n_p + 4});
                     put(p + "/ep", R.ep.data(), {R.n_x + 4, R.n_p + 4});
                 }
+#endif
             }
         }
     }

@@ -1,0 +1,81 @@
+"""Drop-in test of the C++ host layer (veritas_b200/host/): ONE case file (oracle/ref_harness.cpp, playing the role of the
+reference's veritas.cpp) is compiled twice — against the unmodified reference classes (oracle/_ref/ref_harness, CPU) and
+against the veritas_b200 host classes + libveritas_b200.so (oracle/_ref/host_harness, GPU).  Both run the same Settings
+free-running through the fields-only phase and N Vlasov steps with regridding; their full-precision dumps must agree:
+identical hierarchies after every regrid (host clustering = the reference's), f and fields within tolerance."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from common import rel_l2
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle.dumpio import read_dump  # noqa: E402
+from oracle.port import hierarchy_from_dump  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+REF = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+HOST = os.path.join(ROOT, "oracle", "_ref", "host_harness")
+
+
+def run_both(tmp_path, args):
+    outs = {}
+    for name, exe in (("ref", REF), ("host", HOST)):
+        if not os.path.exists(exe):
+            pytest.fail(f"{exe} missing: run __graft_entry__.build() in the build container")
+        path = str(tmp_path / f"{name}.bin")
+        env = dict(os.environ, OPENBLAS_NUM_THREADS="1")
+        r = subprocess.run([exe, path] + args, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:]
+        outs[name] = read_dump(path)
+    return outs["ref"], outs["host"]
+
+
+def strip(H):
+    return [[{k: v for k, v in p.items()} for p in h] for h in H]
+
+
+def compare(ref, host, steps, tol_f, tol_fields):
+    worst = {"f": 0.0, "fields": 0.0, "PHI": 0.0}
+    most = 0
+    for n in range(0, steps + 1):
+        tag = f"step{n}"
+        Hr, Hh = hierarchy_from_dump(ref, tag), hierarchy_from_dump(host, tag)
+        assert strip(Hr) == strip(Hh), (tag, "hierarchies differ", strip(Hr), strip(Hh))
+        most = max(most, max(len(h) for h in Hr))
+        for s in range(2):
+            for p in Hr[s]:
+                a, b = host[f"{tag}/{p['key']}/f"], ref[f"{tag}/{p['key']}/f"]
+                for state in (0, 1):
+                    e = rel_l2(a[:, :, state], b[:, :, state])
+                    worst["f"] = max(worst["f"], e)
+                    assert e < tol_f, (tag, p["key"], state, e)
+        for k in ("By", "Bz", "Ey", "Ez", "Ay", "Az"):
+            e = rel_l2(host[f"{tag}/{k}"][0], ref[f"{tag}/{k}"][0])
+            worst["fields"] = max(worst["fields"], e)
+            assert e < tol_fields, (tag, k, e)
+        assert host[f"{tag}/time"][0] == ref[f"{tag}/time"][0]
+        worst["PHI"] = max(worst["PHI"], rel_l2(host[f"{tag}/PHI"], ref[f"{tag}/PHI"]))
+        if n > 0:
+            assert abs(host[f"{tag}/dt"][0] - ref[f"{tag}/dt"][0]) <= 1e-12 * ref[f"{tag}/dt"][0]
+    return worst, most
+
+
+def test_host_layer_single_level_fused(tmp_path):
+    """Lfinest = 1: the host classes pick the fused streaming path; 4 free-running steps after the fields-only phase."""
+    ref, host = run_both(tmp_path, ["96", "48", "1", "0.5", "4", "pre_steps=1600", "threads=4"])
+    worst, _ = compare(ref, host, 4, 1e-12, 1e-12)
+    print("single level, 4 free-running steps: worst relative L2", {k: "%.2e" % v for k, v in worst.items()})
+
+
+def test_host_layer_amr_with_regrid(tmp_path):
+    """Lfinest = 3, regrid every 2 steps (BASELINE config 4 shape): initial hierarchy construction, error flagging, clustering,
+    old->new data transfer on the host; all numerics on the GPU."""
+    ref, host = run_both(tmp_path, ["48", "32", "3", "0.5", "9", "pre_steps=1600", "regrid_every=2", "threads=4"])
+    worst, most = compare(ref, host, 9, 1e-10, 1e-12)
+    assert most >= 4
+    print("3 levels, regrid every 2 steps, 9 free-running steps: worst relative L2", {k: "%.2e" % v for k, v in worst.items()}, "max patches/level", most)

@@ -441,6 +441,16 @@ static int ready(vrt_ctx* c) {
     return 0;
 }
 
+// per-species calls only need that species' hierarchy (SolverManager constructs the meshes one after the other)
+static int ready_species(vrt_ctx* c, int s) {
+    if (!c) return VRT_ERR_ARG;
+    if (!c->grid_set) { c->err = "grid not set"; return VRT_ERR_STATE; }
+    if (s < 0 || s >= c->n_species) { c->err = "bad species index"; return VRT_ERR_ARG; }
+    if (c->S[s].desc.empty()) { c->err = "hierarchy not set for this species"; return VRT_ERR_STATE; }
+    cudaSetDevice(c->device);
+    return 0;
+}
+
 static int moments_impl(vrt_ctx* c) {
     int r;
     if ((r = vrt_fields_assemble_begin(c))) return r;
@@ -453,6 +463,25 @@ static int moments_impl(vrt_ctx* c) {
 }
 
 int vrt_moments(vrt_ctx* c) { if (int r = ready(c)) return r; return moments_impl(c); }
+
+int vrt_moments_species(vrt_ctx* c, int s, double* charge_host, double* j_host) {
+    if (int r = ready(c)) return r;
+    if (!check(c, s >= 0 && s < c->n_species && charge_host && j_host, "vrt_moments_species: bad arguments")) return VRT_ERR_ARG;
+    if (!check(c, c->n_ranks == 1, "vrt_moments_species: single-rank contexts only")) return VRT_ERR_STATE;
+    // the species' contribution alone: charges[s] and the total current are rebuilt from this species only, copied out,
+    // and the assembled state (all species) is restored by a full vrt_moments afterwards
+    int r;
+    if ((r = vrt_fields_assemble_begin(c))) return r;
+    r = (c->S[s].path == VRT_PATH_FUSED) ? vrt_fused_moments(c, s) : vrt_split_moments(c, s);
+    if (r) return r;
+    const int N = c->F.N;
+    std::vector<double> a(N), b(N);
+    VRT_CUDA(c, cudaMemcpyAsync(a.data(), c->S[s].d_charges, sizeof(double) * N, cudaMemcpyDeviceToHost, c->stream));
+    VRT_CUDA(c, cudaMemcpyAsync(b.data(), c->F.J, sizeof(double) * N, cudaMemcpyDeviceToHost, c->stream));
+    VRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < N; i++) { charge_host[i] += a[i]; j_host[i] += b[i]; }
+    return moments_impl(c);
+}
 
 int vrt_enforce_neutralization(vrt_ctx* c) {
     if (int r = ready(c)) return r;
@@ -488,7 +517,7 @@ static int vlasov_stage_impl(vrt_ctx* c, int s, const double* d_dt, int step) {
 }
 
 int vrt_vlasov_stage(vrt_ctx* c, int s, double dt, int step) {
-    if (int r = ready(c)) return r;
+    if (int r = ready_species(c, s)) return r;
     if (!check(c, s >= 0 && s < c->n_species && step >= 0 && step <= 5, "vrt_vlasov_stage: bad arguments")) return VRT_ERR_ARG;
     if (int r = set_params_async(c, dt, nullptr)) return r;
     if (step == 0) if (int r = vrt_fields_snapshot_stage0(c)) return r;
@@ -496,7 +525,7 @@ int vrt_vlasov_stage(vrt_ctx* c, int s, double dt, int step) {
 }
 
 int vrt_vlasov_substep(vrt_ctx* c, int s, int depth, double dt, int step, int substep) {
-    if (int r = ready(c)) return r;
+    if (int r = ready_species(c, s)) return r;
     if (!check(c, s >= 0 && s < c->n_species && step >= -1 && step <= 5, "vrt_vlasov_substep: bad arguments")) return VRT_ERR_ARG;
     if (!check(c, c->S[s].path == VRT_PATH_SPLIT, "vrt_vlasov_substep: sub-steps exist on the split path only (vrt_set_path)")) return VRT_ERR_STATE;
     if (int r = set_params_async(c, dt, nullptr)) return r;
@@ -504,12 +533,18 @@ int vrt_vlasov_substep(vrt_ctx* c, int s, int depth, double dt, int step, int su
 }
 
 int vrt_push_data(vrt_ctx* c, int s, int val) {
-    if (int r = ready(c)) return r;
+    if (int r = ready_species(c, s)) return r;
     if (!check(c, s >= 0 && s < c->n_species && (val == 1 || val == 2), "vrt_push_data: bad arguments")) return VRT_ERR_ARG;
     return push_data_impl(c, s, val);
 }
+int vrt_level_push(vrt_ctx* c, int s, int depth, int update_type, int val) {
+    if (int r = ready_species(c, s)) return r;
+    if (!check(c, s >= 0 && s < c->n_species && (val == 1 || val == 2 || update_type >= 4), "vrt_level_push: bad arguments")) return VRT_ERR_ARG;
+    if (!check(c, c->S[s].path == VRT_PATH_SPLIT, "vrt_level_push: per-level passes exist on the split path only")) return VRT_ERR_STATE;
+    return vrt_amr_level_pass(c, s, depth, update_type, val);
+}
 int vrt_push_boundary_c(vrt_ctx* c, int s) {
-    if (int r = ready(c)) return r;
+    if (int r = ready_species(c, s)) return r;
     if (!check(c, s >= 0 && s < c->n_species, "vrt_push_boundary_c: bad arguments")) return VRT_ERR_ARG;
     if (c->S[s].path == VRT_PATH_FUSED) return 0;   // the fused kernel carries the limiter across its own tiles
     return vrt_amr_push_boundary_c(c, s);
@@ -615,7 +650,7 @@ int vrt_set_option(vrt_ctx* c, int option, int value) {
 }
 
 int vrt_init_maxwellian_slab(vrt_ctx* c, int s, double xl, double xr, double n0, double T, int quadrature_depth) {
-    if (int r = ready(c)) return r;
+    if (int r = ready_species(c, s)) return r;
     if (!check(c, s >= 0 && s < c->n_species, "vrt_init_maxwellian_slab: bad species")) return VRT_ERR_ARG;
     return vrt_init_kernels_maxwellian(c, s, xl, xr, n0, T, quadrature_depth);
 }

@@ -507,55 +507,59 @@ int vrt_amr_upload_connectivity(vrt_ctx* c, int s, const vrt_conn& C) {
 
 static unsigned blocks(long n, int b = 128) { return (unsigned)((n + b - 1) / b); }
 
-// Mesh::PushData(val) (Mesh.cpp:91-106)
-int vrt_amr_push_data(vrt_ctx* c, int s, int val) {
+// Level::PushData(updateType, val) (Level.cpp:88-126): 0 restriction, 1 same-level strips, 2 coarser-level strips + corners,
+// 3 corners, 4 / 5 / 6 the three limiter-sync passes
+int vrt_amr_level_pass(vrt_ctx* c, int s, int l, int type, int val) {
     VrtSpeciesState& S = c->S[s];
     const int nl = (int)S.level_patches.size(), r = c->refinement_ratio;
+    if (l < 0 || l >= nl || type < 0 || type > 6) { c->err = "level pass: bad level or update type"; return VRT_ERR_ARG; }
+    const std::vector<int>& lp = S.level_patches[l];
+    if (lp.empty()) return 0;
     const VrtPatchDev* all = S.d_patches;
-    auto perim = [&](int l) { long m = 0; for (int p : S.level_patches[l]) m = std::max<long>(m, 2L * S.table[p].n_x + 2L * S.table[p].n_p); return m; };
-    auto strips = [&](int l) { long m = 0; for (int p : S.level_patches[l]) m = std::max<long>(m, 2L * (S.table[p].ns_x - 2) + 2L * S.table[p].ns_p); return m; };
-    auto npadmax = [&](int l) { long m = 0; for (int p : S.level_patches[l]) m = std::max(m, S.table[p].npad); return m; };
-    auto same_pass = [&](int l) {
-        if (S.level_patches[l].empty()) return;
-        k_ghost_same<<<dim3(blocks(perim(l)), (unsigned)S.level_patches[l].size()), 128, 0, c->stream>>>(all + S.level_patches[l][0], all, val, r);
-        c->launches += 1;
-    };
-    same_pass(0);
-    for (int l = 1; l < nl; l++) {
-        if (!S.level_patches[l].empty() && !S.level_patches[l - 1].empty()) {
-            k_restrict<<<dim3(blocks(npadmax(l), 256), (unsigned)S.level_patches[l].size()), 256, 0, c->stream>>>(all + S.level_patches[l][0], all, val, r);
-            c->launches += 1;
-        }
-        same_pass(l);
+    const VrtPatchDev* level = all + lp[0];
+    const unsigned np = (unsigned)lp.size();
+    long perim = 0, strips = 0, npad = 0;
+    for (int p : lp) {
+        const VrtPatchDev& T = S.table[p];
+        perim = std::max<long>(perim, 2L * T.n_x + 2L * T.n_p);
+        strips = std::max<long>(strips, 2L * (T.ns_x - 2) + 2L * T.ns_p);
+        npad = std::max(npad, T.npad);
     }
-    if (!S.level_patches[nl - 1].empty()) {
-        k_corners<<<dim3(1, (unsigned)S.level_patches[nl - 1].size()), 32, 0, c->stream>>>(all + S.level_patches[nl - 1][0], all, val, r);
-        c->launches += 1;
+    switch (type) {
+        case 0:
+            if (l == 0 || S.level_patches[l - 1].empty()) return 0;      // nothing is nested without a finer level
+            k_restrict<<<dim3(blocks(npad, 256), np), 256, 0, c->stream>>>(level, all, val, r); break;
+        case 1: k_ghost_same<<<dim3(blocks(perim), np), 128, 0, c->stream>>>(level, all, val, r); break;
+        case 2: k_ghost_coarse<<<dim3(blocks(strips + 8), np), 128, 0, c->stream>>>(level, all, val, r); break;
+        case 3: k_corners<<<dim3(1, np), 32, 0, c->stream>>>(level, all, val, r); break;
+        default:
+            if (!S.has_amr) return 0;     // every strip faces the BoundaryCondition object: zero-trip loops (quirk Q8)
+            k_boundary_c<<<dim3(blocks(strips), np), 128, 0, c->stream>>>(level, all, type, r); break;
     }
-    for (int l = nl - 1; l > 0; l--) {
-        if (S.level_patches[l - 1].empty()) continue;
-        k_ghost_coarse<<<dim3(blocks(strips(l - 1) + 8), (unsigned)S.level_patches[l - 1].size()), 128, 0, c->stream>>>(all + S.level_patches[l - 1][0], all, val, r);
-        c->launches += 1;
-    }
+    c->launches += 1;
     VRT_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+// Mesh::PushData(val) (Mesh.cpp:91-106)
+int vrt_amr_push_data(vrt_ctx* c, int s, int val) {
+    const int nl = (int)c->S[s].level_patches.size();
+    int rc;
+    if ((rc = vrt_amr_level_pass(c, s, 0, 1, val))) return rc;
+    for (int l = 1; l < nl; l++) {
+        if ((rc = vrt_amr_level_pass(c, s, l, 0, val))) return rc;
+        if ((rc = vrt_amr_level_pass(c, s, l, 1, val))) return rc;
+    }
+    if ((rc = vrt_amr_level_pass(c, s, nl - 1, 3, val))) return rc;
+    for (int l = nl - 1; l > 0; l--) if ((rc = vrt_amr_level_pass(c, s, l - 1, 2, val))) return rc;
     return 0;
 }
 
 // Mesh::PushBoundaryC (Mesh.cpp:904-917): passes 4, 5, 6 over all levels, finest first
 int vrt_amr_push_boundary_c(vrt_ctx* c, int s) {
-    VrtSpeciesState& S = c->S[s];
-    if (!S.has_amr) return 0;     // every strip faces the BoundaryCondition object: zero-trip loops (quirk Q8)
-    const int nl = (int)S.level_patches.size(), r = c->refinement_ratio;
-    const VrtPatchDev* all = S.d_patches;
+    const int nl = (int)c->S[s].level_patches.size();
     for (int pass = 4; pass <= 6; pass++)
-        for (int l = 0; l < nl; l++) {
-            if (S.level_patches[l].empty()) continue;
-            long m = 0;
-            for (int p : S.level_patches[l]) m = std::max<long>(m, 2L * (S.table[p].ns_x - 2) + 2L * S.table[p].ns_p);
-            k_boundary_c<<<dim3(blocks(m), (unsigned)S.level_patches[l].size()), 128, 0, c->stream>>>(all + S.level_patches[l][0], all, pass, r);
-            c->launches += 1;
-        }
-    VRT_CUDA(c, cudaGetLastError());
+        for (int l = 0; l < nl; l++) if (int rc = vrt_amr_level_pass(c, s, l, pass, 1)) return rc;
     return 0;
 }
 

@@ -165,6 +165,7 @@ int vrt_split_substep(vrt_ctx* c, int s, int depth, const double* d_dt, int step
 int vrt_split_moments(vrt_ctx* c, int s);
 // AMR kernels (vrt_amr.cu, compiled with -fmad=false)
 int vrt_amr_upload_connectivity(vrt_ctx* c, int s, const vrt_conn& C);
+int vrt_amr_level_pass(vrt_ctx* c, int s, int depth, int type, int val);
 int vrt_amr_push_data(vrt_ctx* c, int s, int val);
 int vrt_amr_push_boundary_c(vrt_ctx* c, int s);
 int vrt_amr_level_boundary_fluxes(vrt_ctx* c, int s, int depth, int step);

@@ -1,0 +1,2 @@
+// forwarding header: a case file written against the reference includes "Settings.hpp"; all declarations live in veritas_host.hpp
+#include "veritas_host.hpp"

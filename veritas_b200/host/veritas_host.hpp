@@ -1,0 +1,279 @@
+// veritas_b200 host layer: the reference's C++ class surface as thin shells over the C ABI of
+// include/veritas_b200.h.  A case file written for the reference (its veritas.cpp: initialConditions, the user-defined
+// Settings members, main) compiles against these declarations unchanged — the forwarding headers veritas.hpp, Settings.hpp,
+// SolverManager.hpp, EMSolver.hpp, Mesh.hpp, Level.hpp, Rectangle.hpp, BoundaryCondition.hpp in this directory all include
+// this file.
+//
+// Division of labour (north_star): the host keeps the AMR hierarchy, the regridding (error flagging, clustering, old->new
+// data transfer), the user callbacks and the text output; every numerical member on the path of SolverManager::Advance is a
+// call into libveritas_b200.so and runs on the GPU.  Rectangle::f and the EMFieldSolver arrays are HOST MIRRORS: the device
+// owns the data between SyncHost() calls (made before regridding and before output).
+//
+// Members the reference declares private keep their names (the oracle harness reads them with -fno-access-control);
+// per-Rectangle numerical methods of the reference (FCTTimeStep, Update*Boundaries, CalculateRhoAndJ, Set*C*, RGKGetFlux*)
+// have no per-patch counterpart: one launch serves all rectangles of a level, so they are reached through Level / Mesh.
+#ifndef VERITAS_B200_HOST_HPP
+#define VERITAS_B200_HOST_HPP
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <iterator>
+#include <limits>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <tuple>
+#include <utility>
+#include <vector>
+#include <omp.h>
+#include "../../include/veritas_b200.h"
+
+// physical constants: the reference's literals (veritas.hpp:22-30; not mutually exact, used verbatim — quirk Q9)
+constexpr double eps0_inv = 1.1294e+11;
+constexpr double eps0 = 8.854187817e-12;
+constexpr double mu = 1.2566370614e-6;
+constexpr double mu_inv = 795774.715482;
+constexpr double cs = 299792458.0;
+constexpr double c_inv = 3.33564095e-9;
+constexpr int eps = 0;
+constexpr double DPI = 6.28318530718;
+constexpr int OUTW = 80;
+#define MKLINIT 0
+
+extern bool LOUD;    // defined by the case file, as in the reference (veritas.cpp:117)
+extern bool NOISY;
+
+typedef std::pair<int, int> coords;         // (x, p) cell index
+typedef std::pair<coords, coords> rect;     // (lower-left, upper-right)
+typedef std::vector<rect> level;
+typedef std::tuple<int, int, double> rectData;
+
+class Rectangle;
+class Level;
+class Mesh;
+class EMFieldSolver;
+class Settings;
+
+// ---- input structs: same fields and defaults as Settings.hpp:4-33 ------------------------------------------------------
+struct Input {
+    double minEfficiency = 0.6, dx = 0.5, k = 0.01;
+    double refinementCriteria = 1e-8, cfl = 0.9, sizeWeight = 0.0;
+    double preLength = 2, postLength = 2;
+    unsigned int nx = 76 * 4, r = 2, Lfinest = 5;
+    double plasma_xl_bound = 3.0e-6, plasma_xr_bound = 7.0e-6;
+    std::vector<double> tempEM = {0.0};
+};
+struct Particles {
+    std::vector<double> mass = {9.10938291e-31};
+    std::vector<double> charge = {-1.60217657e-19};
+    std::vector<std::vector<double>> misc = {{0.0, 0.01}};
+    std::vector<unsigned int> np = {50};
+    std::vector<double> dp = {0.1};
+    std::vector<double> pmin = {0.1};
+};
+struct Output {
+    bool time = true, rectangleData = true, charge = true, energy = true, potential = true;
+    bool EFieldLongitudinal = true, EFieldTransverse = true, BFieldTransverse = true, AFieldSquared = true;
+    int precision = 15;
+};
+
+// ---- Settings (Settings.hpp:35-65) ----------------------------------------------------------------------------------------
+class Settings {
+    vrt_ctx* gpu_ = nullptr;
+    int device_ = 0;
+public:
+    Output output;
+    double dx, time, minEfficiency, preLength, postLength, refinementCriteria, cfl, sizeWeight, plasma_xl_bound, plasma_xr_bound;
+    std::vector<double> m, q, m_inv, dp, fMax, tempEM, pmin;
+    std::vector<std::vector<double>> temp;
+    unsigned int x_size_finest, x_size, refinementRatio;
+    int maxDepth, quadratureDepth;
+    std::vector<unsigned int> p_size, p_size_finest;
+
+    Settings(const Input& grid, const Particles& particles, const Output& out);
+    ~Settings();
+    Settings(const Settings&) = delete;
+    Settings& operator=(const Settings&) = delete;
+
+    void title(std::string output, char spacer);
+    double GetDp(int level, int particleType);
+    double GetDx(int level);
+    int GetXSize(int level);
+    int GetPSize(int level, int particleType);
+    double GetMass(int i);
+    double GetCharge(int i);
+    double GetfMax(int i);
+    void UpdateTime(int step, double dt);
+    void DetermineMaximum();
+    // user-defined in the case file, exactly as for the reference (Settings.hpp:47,59-60,63-64)
+    double InitialDistribution(double x, double p, int particleType);
+    double GetBY(double x, double t);
+    double GetBZ(double x, double t);
+    void settingsOverride();
+    bool RefinementOverride(double x, double p, int depth, int particleType);
+
+    // veritas_b200 additions
+    vrt_ctx* Gpu();                  // the device context of this run, created on first use (VRT_DEVICE selects the GPU)
+    int PrePad();                    // EMFieldSolver::n_prepad / n_postpad (EMSolver.cpp:7-8)
+    int PostPad();
+    void Check(int rc, const char* what);   // reference error convention: message on std::cerr + exit(EXIT_FAILURE)
+};
+
+// ---- Rectangle (Rectangle.hpp:6-80): host descriptor + mirror of one patch ----------------------------------------------------
+class Rectangle {
+protected:
+    std::vector<double> errorWeights, interpolationMatrix, interpolatCoefsREF;
+    std::vector<bool> is_interpolated;
+    int refinementRatio, depth, particleType;
+    double dp, dx, m_inv;
+    Settings* settings_;
+    bool up, down, left, right;
+public:
+    int n_x, n_p, x_pos, p_pos;
+    double relativeToBottom;
+    std::vector<double> f, chargeR, energyR, currentR;     // f: 3 states per padded cell, AoS (Rectangle.hpp:96-98)
+    int patch_id = -1;                                      // number of this patch in vrt_set_hierarchy
+
+    Rectangle(int n_x, int n_p, int x_pos, int p_pos, int depth, Settings& settings, const std::shared_ptr<Rectangle>& bc,
+              bool up, bool down, bool left, bool right, int particleType);
+    Rectangle();
+    virtual ~Rectangle();
+    inline int Index3(int i, int j, int state) const { return 3 * ((n_p + 4) * (i + 2) + 2 + j) + state; }
+    inline int IndexNS(int i, int j) const { return (n_p + 4) * (i + 2) + 2 + j; }
+    inline int GetFinestIndex(int i) const { return (int)(relativeToBottom * (i + x_pos)); }
+    inline double Momentum(double i) const;
+    virtual double GetValueFromSameLevel(int i, int j, int val = 1);
+    void InitializeDistribution();
+    void getError(std::vector<coords>& flaggedCells, int particleType);
+    inline double ErrorEstimate(int i, int j);
+    std::vector<double> GetInterpolantsREF(double f1, double f2, double f3, double f4, double f5);
+    std::vector<double> GetWenoValueFromCoarseLevel(int i, int j, int d, int val = 1);
+    void GetDataFromCoarseLevelRectangle(const std::shared_ptr<Rectangle>& rectangle);
+    void GetDataFromSameLevelRectangle(const std::shared_ptr<Rectangle>& rectangle);
+    void GetDataFromCoarseNewLevelRectangle(const std::shared_ptr<Rectangle>& rectangle);
+    vrt_patch_desc Descriptor() const;
+    int Depth() const { return depth; }
+};
+
+class BoundaryCondition : public Rectangle {     // BoundaryCondition.hpp:7-11: the domain ghost value
+public:
+    ~BoundaryCondition();
+    virtual double GetValueFromSameLevel(int i, int j, int val = 1.0);
+};
+
+// ---- Level (Level.hpp:4-23) -------------------------------------------------------------------------------------------------
+class Level {
+    int x_size, p_size, depth, particleType;
+    Settings& settings;
+public:
+    std::vector<std::shared_ptr<Rectangle>> rectangles;
+    Level(int particleType, int depth, Settings& settings);
+    void FCTTimeStep(double timestep, int step, int subStep);
+    void PushData(int updateType, int val = 1);
+    void GetDataFromSameLevel(const std::unique_ptr<Level>& level);
+    void GetDataFromCoarserLevel(const std::unique_ptr<Level>& level);
+    void GetDataFromCoarseNewLevel(const std::unique_ptr<Level>& level);
+};
+
+// ---- Mesh (Mesh.hpp:4-41): one species, hierarchy + regridding on the host ------------------------------------------------------
+class Mesh {
+    std::vector<level> hierarchy;
+    Settings& settings;
+    std::shared_ptr<EMFieldSolver> EMSolver;
+    std::shared_ptr<Rectangle> bc;
+    bool device_current_ = false;      // the device holds newer data than Rectangle::f
+public:
+    int particleType;
+    std::vector<std::unique_ptr<Level>> levels;
+    Mesh(int particleType, Settings& settings);
+    void PushData(int val = 1);
+    void Advance(double timeStep, int step);
+    void PushBoundaryC();
+    void InterpolateRhoAndJToFinestMesh(std::vector<double>& charge, std::vector<double>& J);
+    void SetFieldSolver(const std::shared_ptr<EMFieldSolver>& solver);
+    void updateHierarchy(bool init = false);
+    void outputRectangleData(double tidx);
+    // clustering (Mesh.cpp:341-792)
+    int countCells(const rect& span);
+    std::tuple<std::vector<int>, std::vector<int>, std::vector<int>, std::vector<int>> computeSignatures(rect& rectangle, std::vector<coords>& flagged);
+    coords identifyInflection(rect& rectangle, std::tuple<std::vector<int>, std::vector<int>, std::vector<int>, std::vector<int>>& signatures);
+    std::tuple<bool, int, int> hasHole(std::vector<int>& sig);
+    level splitRectangle(rect& rectangle, std::vector<coords>& flagged, const double& minEfficiency);
+    void getError(const int& lvl, bool init, std::vector<coords>& flaggedCells);
+    void interpRectanglesUp(level& identified, const int& lvl);
+    void mergeDownFlaggedData(const int& lvl, const rect& r, std::vector<coords>& foundCells);
+    void getExtrema(rect& extrema, const std::vector<coords>& flaggedCells);
+    void promoteHierarchyToMesh(bool init);
+    void InterMeshDataTransfer(const std::vector<std::unique_ptr<Level>>& levels_n);
+    // veritas_b200 additions
+    void SyncHost();                   // device -> Rectangle::f (states 0 and 1, ghosts included)
+    void MarkDeviceCurrent() { device_current_ = true; }
+    const std::vector<level>& Hierarchy() const { return hierarchy; }
+};
+
+// ---- EMFieldSolver (EMSolver.hpp:9-63) ---------------------------------------------------------------------------------------------
+class EMFieldSolver {
+    Settings& settings;
+    int n_prepad, n_postpad;
+    unsigned int x_size;
+    std::vector<std::shared_ptr<Mesh>> meshes;
+    std::ofstream *chargeStream, *ELongStream, *ETransStream, *potentialStream, *BStream, *AsqStream, *timeStream;
+    std::vector<double> charge, J, By, Bz, Ey, Ez, Ay, Az, a_squared, neutralizationCharge;   // host mirrors
+    std::vector<std::vector<double>> charges;
+    double* PHI;
+    double fieldCoef, Ex0;
+    bool mirrors_current_ = false;
+public:
+    EMFieldSolver(Settings& settings, const std::vector<std::shared_ptr<Mesh>>& meshes);
+    ~EMFieldSolver();
+    void AssembleRhoAndJ();
+    void AssembleEnergy();
+    void UpdatePotential();
+    void RGKStep(int step, double timestep);
+    double GetASquared(int i);
+    double GetEfield(int i);
+    double GetCellAverageASquared(int i);
+    double EstimateCFLBound();
+    void EnforceChargeNeutralization();
+    void DumpCharge();
+    void DumpEnergy();
+    void DumpEFieldLongitudinal();
+    void DumpEFieldTransverse();
+    void DumpPotential();
+    void DumpBFieldTransverse();
+    void DumpAsqField();
+    void DumpTime(double time);
+    inline int Index(int i, int step) { return step * (x_size + n_prepad + n_postpad) + i; }
+    // veritas_b200 additions
+    void SyncHost();                   // device -> the mirrors above
+    void Invalidate() { mirrors_current_ = false; }
+};
+
+// ---- SolverManager (SolverManager.hpp:5-19) -------------------------------------------------------------------------------------------
+class SolverManager {
+    std::shared_ptr<EMFieldSolver> EMSolver;
+    Settings& settings;
+    std::vector<std::shared_ptr<Mesh>> meshes;
+    void StageLasers(double timeStep, double laser[12]);
+public:
+    SolverManager(Settings& settings);
+    void Advance(double timeStep);
+    void AdvanceFields(double timeStep);
+    void reGrid(double t);
+    std::string centeredOutput(std::string const& original, int targetSize);
+    void screenOutput(const std::shared_ptr<Mesh>& mesh);
+    void OutputRectangles(double t);
+    void fileOutput(double t);
+    double CalculateDt(double cfl);
+    // veritas_b200 addition: refresh every host mirror (Rectangle::f, EMFieldSolver arrays) from the device
+    void SyncHost();
+};
+
+inline double Rectangle::Momentum(double i) const { return settings_->pmin[particleType] + dp * (i + p_pos); }
+
+#endif  // VERITAS_B200_HOST_HPP
