@@ -206,6 +206,7 @@ int vrt_set_hierarchy(vrt_ctx* c, int s, int n_patches, const vrt_patch_desc* d)
         // (VRT_SLAB_GH + j0 - 3, j0 even) 16-byte aligned for the bulk-async (TMA) column loads
         L.gx = 3; L.pitch = ((q0.n_p + VRT_SLAB_GH + 4 + 1) / 2) * 2;
         L.plane = (long)(L.n_x + 2 * L.gx) * L.pitch + 1024;   // slack: the last strip's bulk load may run past the last column
+        if (!check(c, L.plane < (1L << 31), "vrt_set_hierarchy: slab plane exceeds 2^31 cells (split the domain over more GPUs)")) return VRT_ERR_ARG;
         L.dx = c->F.dx; L.dp = sp.dp_finest;
         for (int k = 0; k < 3; k++) if ((rc = dev_alloc(c, S.allocations, &L.f[k], L.plane))) return rc;
         for (int k = 0; k < 5; k++) {
