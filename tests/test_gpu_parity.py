@@ -192,3 +192,21 @@ def test_particle_number_conserved_at_scale():
         n1 = run.ctx.download_f(s, 0, 1)[2:-2, 2:-2].sum()
         assert abs(n1 - n0[s]) <= 1e-12 * abs(n0[s]), (s, n0[s], n1)
     run.ctx.close()
+
+
+def test_fused_equals_split_interior_tiles():
+    """A mesh large enough for the fused kernel's interior-CTA specialisation (compile-time CTA width, no boundary predicates)
+    and its edge CTAs to coexist: 3 free-running steps with the laser inside the plasma, fused vs the bit-faithful split path."""
+    res = {}
+    for path in (S.PATH_SPLIT, S.PATH_FUSED):
+        run = vb.LaserPlasmaRun(640, 512, density=0.3, path=path)
+        run.init_device()
+        run.run_fields_phase()
+        for _ in range(3):
+            run.advance(run.calculate_dt())
+        res[path] = [run.ctx.download_f(s, 0, 1) for s in range(2)] + [run.ctx.download_field(S.EY, 0), run.ctx.get_1d(S.J)]
+        assert run.ctx.get_path(0) == path
+        run.ctx.close()
+    errs = [rel_l2(b, a) for a, b in zip(res[S.PATH_SPLIT], res[S.PATH_FUSED])]
+    print("fused vs split, 640x512, 3 steps: f_e %.2e f_i %.2e Ey %.2e J %.2e" % tuple(errs))
+    assert errs[0] < 1e-12 and errs[1] < 1e-12 and errs[2] < 1e-12 and errs[3] < 1e-10
