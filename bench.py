@@ -177,8 +177,9 @@ def main():
         from veritas_b200.parallel import broadcast_unique_id
         ctx.call("vrt_comm_init", broadcast_unique_id(dist, run.L, rank, device="cuda"), rank, n_gpus)
     run.init_device()
+    fields_steps = 0
     if not args.skip_fields_phase:
-        run.run_fields_phase()          # veritas.cpp:139-144: the laser enters the box while the plasma is frozen
+        fields_steps = run.run_fields_phase()          # veritas.cpp:139-144: the laser enters the box while the plasma is frozen
     else:
         run.time = 3 * run.T
     ctx.sync()
@@ -190,6 +191,13 @@ def main():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def species_charge():
+        """sum over x of each species' charge density (= q N / dx): conserved to round-off by the flux form with closed walls"""
+        ctx.moments()
+        return [float(np.sum(ctx.get_1d(S.CHARGES0 + s))) for s in range(2)]
+
+    q0 = species_charge()
 
     # ---- warm-up --------------------------------------------------------------------------------------------------
     dt = run.calculate_dt()
@@ -242,19 +250,27 @@ def main():
     tot_bytes, tot_ms, per_stage = 0.0, 0.0, []
     reps = 2
     ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(12)] for _ in range(reps)]
+    other = {"moments": [], "poisson": [], "field_stage": []}
+
+    def timed(name, fn):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream); fn(); b.record(stream)
+        other[name].append((a, b))
+
     for r in range(reps):
         lasers, tnew = run.stage_lasers(dt)
         k = 0
         for i in range(6):
-            ctx.moments(); ctx.poisson()
+            timed("moments", ctx.moments); timed("poisson", ctx.poisson)
             for s in range(2):
                 a, b = ev[r][k]; k += 1
                 a.record(stream)
                 ctx.vlasov_stage(s, dt, i)
                 b.record(stream)
-            ctx.field_stage(i, dt, lasers[2 * i], lasers[2 * i + 1])
+            timed("field_stage", lambda: ctx.field_stage(i, dt, lasers[2 * i], lasers[2 * i + 1]))
         run.time = tnew
     barrier()
+    breakdown = {k: round(sum(a.elapsed_time(b) for a, b in v) / reps, 3) for k, v in other.items()}
     for i in range(6):
         msl = [ev[r][2 * i + s][0].elapsed_time(ev[r][2 * i + s][1]) for r in range(reps) for s in range(2)]
         avg = sum(msl) / len(msl)
@@ -270,6 +286,17 @@ def main():
                 "traffic": None, "kernel": "k_fused_stage<S> (76 B/cell/stage algorithmic, averaged over the 6 stages)",
                 "per_stage_GBps": per_stage, "peak_source": peak_src,
                 "stage_cell_updates_per_s": round(6 * cells_loc / (tot_ms * 1e-3), 1)}
+    breakdown["fused_stage"] = round(2 * tot_ms, 3)     # both species
+    run_steps = args.warmup + 2 * args.steps + reps
+
+    # ---- sanity of the state the numbers were measured on ---------------------------------------------------------------
+    q1 = species_charge()
+    fields_ok = all(bool(np.all(np.isfinite(ctx.get_1d(w)))) for w in (S.CHARGE, S.J, S.A_SQUARED, S.EFIELD))
+    fields_ok = fields_ok and bool(np.all(np.isfinite(ctx.download_field(S.EY, 0))))
+    drift = [abs(b - a) / abs(a) for a, b in zip(q0, q1)]
+    a2max = float(np.max(ctx.get_1d(S.A_SQUARED)))
+    if not fields_ok or not all(np.isfinite(drift)) or max(drift) > 1e-9:
+        raise SystemExit(f"bench.py: state is not finite / particle number drifted ({drift}); the measurement is void")
 
     if rank == 0:
         cb = None if args.no_cpu_baseline else cpu_baseline()
@@ -285,6 +312,9 @@ def main():
                     "what": "CalculateDt + Advance + 1-D output arrays per step through the C ABI with host buffers; f stays resident as in the reference"},
             "gpu_launches": int(launches),
             "roofline": roofline,
+            "breakdown_ms_per_step": breakdown,
+            "checks": {"finite": fields_ok, "particle_number_rel_drift": drift, "max_a_squared": a2max,
+                       "fields_phase_steps": fields_steps, "steps_run": run_steps},
             "cpu_baseline": cb,
         }
         print(json.dumps(out))

@@ -210,3 +210,83 @@ def test_fused_equals_split_interior_tiles():
     errs = [rel_l2(b, a) for a, b in zip(res[S.PATH_SPLIT], res[S.PATH_FUSED])]
     print("fused vs split, 640x512, 3 steps: f_e %.2e f_i %.2e Ey %.2e J %.2e" % tuple(errs))
     assert errs[0] < 1e-12 and errs[1] < 1e-12 and errs[2] < 1e-12 and errs[3] < 1e-10
+
+
+def test_moment_kernel_variants_long_columns(monkeypatch):
+    """Rectangle::CalculateRhoAndJ on slab storage at a column length that needs more than one pass of the streaming
+    kernel (n_p = 4608 > 33 x 128), with the laser inside the plasma (a^2 != 0): every tiling of the fused-path kernel
+    against the split path's per-patch kernel, which is checked against the oracle and the reference dumps above."""
+    res = {}
+    for key, path, var in (("split", S.PATH_SPLIT, "0"), ("33x128", S.PATH_FUSED, "0"), ("17x256", S.PATH_FUSED, "1"), ("forced", S.PATH_FUSED, "2")):
+        monkeypatch.setenv("VRT_MOM_VAR", var)
+        run = vb.LaserPlasmaRun(192, 4608, density=0.3, path=path)
+        run.init_device()
+        run.run_fields_phase()
+        run.ctx.moments()
+        # per-species charges: the total is a difference of the two species' sums (quasi-neutral cancellation)
+        res[key] = (run.ctx.get_1d(S.CHARGES0), run.ctx.get_1d(S.CHARGES0 + 1), run.ctx.get_1d(S.J))
+        run.ctx.close()
+    assert np.abs(res["split"][2]).max() > 0
+    for key in ("33x128", "17x256", "forced"):
+        errs = [rel_l2(a, b) for a, b in zip(res[key], res["split"])]
+        print(f"moments {key} vs split: charge e- {errs[0]:.2e} p+ {errs[1]:.2e} J {errs[2]:.2e}")
+        assert max(errs) < 1e-12
+
+
+def test_moment_kernel_variants_short_columns(monkeypatch):
+    """The same kernels with most threads masked (n_p = 64): J and charge of a reference state against the reference's dump."""
+    d = load_golden("single_64x32_stages")
+    for var in ("0", "1", "2"):
+        monkeypatch.setenv("VRT_MOM_VAR", var)
+        ctx, mt = make_ctx(d, S.PATH_FUSED)
+        ctx.load_reference_state(d, "step0")
+        ctx.moments()
+        for which, k in ((S.J, "J"), (S.CHARGE, "charge")):
+            e = rel_l2(ctx.get_1d(which), d["step1_stage0/" + k])
+            assert e < 1e-11, (var, k, e)
+        ctx.close()
+
+
+def test_poisson_tiled_solver_at_scale():
+    """UpdatePotential at a size the dense LU cannot reach (N = 65536 + 38: 65 tiles, ragged last tile): the O(N) device
+    solve against an extended-precision evaluation of the same linear system A x = b (EMSolver.cpp:28-67: column 0 = e_0,
+    the other columns the periodic 4th-order -d2 stencil), whose residual is verified here first."""
+    rng = np.random.default_rng(11)
+    N = 65536 + 38
+    dx = 1e-5 / N
+    ld = np.longdouble
+    rho = rng.standard_normal(N) * 1e3
+    rho -= rho.mean()
+    neutral = rng.standard_normal(N) * 1e-3
+    b = (ld(S.EPS0_INV) * (rho.astype(ld) + neutral.astype(ld))) * (ld(dx) * ld(dx))
+    sb = b.sum()
+    bp = b.copy(); bp[0] -= sb
+    # extended-precision solve: T z = b', D y = z with y_0 = 0 (L = T D), T^-1 by its geometric Green's function
+    r = ld(1) / (ld(7) + np.sqrt(ld(48))); Cg = ld(6) / np.sqrt(ld(48))
+    z = Cg * bp
+    for k in range(1, 40):
+        z = z + Cg * r ** k * (np.roll(bp, k) + np.roll(bp, -k))
+    c = np.cumsum(z)
+    dd = c.mean() - c
+    y = np.concatenate(([ld(0)], np.cumsum(dd)[:-1]))
+    Ly = (ld(5) / 2) * y - (ld(4) / 3) * (np.roll(y, 1) + np.roll(y, -1)) + (ld(1) / 12) * (np.roll(y, 2) + np.roll(y, -2))
+    assert float(np.abs(Ly - bp).max() / np.abs(bp).max()) < 1e-9       # the comparison solution solves the reference's system
+    phi_ref = y.copy(); phi_ref[0] = sb
+    ctx = vb.Context(1)
+    ctx.set_grid(N, dx, 2, 2, 2, 0)
+    ctx.set_species(0, S.M_E, -S.Q_E, -1.0e-21, 1e-23)
+    ctx.set_1d(S.CHARGE, rho); ctx.set_1d(S.NEUTRALIZATION, neutral)
+    ctx.set_scalar(S.EX0, 0.0)
+    ctx.call("vrt_set_hierarchy", 0, 1, (vb.PatchDesc * 1)(vb.PatchDesc(depth=0, x_pos=0, p_pos=0, n_x=N, n_p=8, up=1, down=1, left=1, right=1)))
+    ctx.poisson()
+    phi = ctx.get_1d(S.PHI); E = ctx.get_1d(S.EFIELD); ex0 = ctx.get_scalar(S.EX0)
+    # GetEfield reads PHI including the gauge entry PHI_0 = sum(b) (EMSolver.cpp:137-154)
+    pr = phi_ref
+    Eb = -(8 * (np.roll(pr, -1) - np.roll(pr, 1)) - np.roll(pr, -2) + np.roll(pr, 2)) / (12 * ld(dx))
+    ex0_ref = -(Eb[-1] + Eb[0]) / 2
+    e_phi = rel_l2(phi[1:], phi_ref[1:].astype(np.float64))
+    e_E = rel_l2(E, (Eb + ex0_ref).astype(np.float64))
+    print(f"tiled Poisson N={N}: PHI {e_phi:.2e}  E {e_E:.2e}  Ex0 {ex0:.6e} vs {float(ex0_ref):.6e}")
+    assert e_phi < 1e-9 and e_E < 1e-8
+    assert abs(phi[0] - float(sb)) <= 1e-9 * float(np.abs(b).sum())
+    ctx.close()

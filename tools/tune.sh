@@ -4,7 +4,7 @@ run() { python bench.py --steps 3 --warmup 3 --no-cpu-baseline "$@" 2>&1 | tail 
 import sys,json
 try:
     d=json.loads(sys.stdin.read()); r=d['roofline']
-    print('value=%.3e stage=%.3e frac=%.4f ms/step=%.1f per_stage=%s clocks=%s'%(d['value'],r['stage_cell_updates_per_s'],r['frac'],d['ms_per_step'],r['per_stage_GBps'],d['clocks']))
+    print('value=%.3e e2e=%.3e stage=%.3e frac=%.4f ms/step=%.1f per_stage=%s breakdown=%s clocks=%s'%(d['value'],d['e2e']['value'],r['stage_cell_updates_per_s'],r['frac'],d['ms_per_step'],r['per_stage_GBps'],d.get('breakdown_ms_per_step'),d['clocks']))
 except Exception as e: print('ERR',e)
 "; }
 for cfg in "$@"; do

@@ -134,7 +134,7 @@ int vrt_set_grid(vrt_ctx* c, int N, double dx, int pre, int post, int r, int max
     if ((rc = dev_alloc(c, c->field_allocs, &F.J, N))) return rc;
     if ((rc = dev_alloc(c, c->field_allocs, &F.neutral, N))) return rc;
     if ((rc = dev_alloc(c, c->field_allocs, &F.Ex0, 2))) return rc;
-    if ((rc = dev_alloc(c, c->field_allocs, &F.scratch, 4L * N))) return rc;
+    if ((rc = dev_alloc(c, c->field_allocs, &F.scratch, 4L * N + 8 + 4 * 4096))) return rc;   // 3 N-vectors + sum(b) + Poisson tile partials (vrt_fields.cu); level moments use the first 2N
     if ((rc = dev_alloc(c, c->field_allocs, &F.cfl, 2))) return rc;
     for (auto& S : c->S) { double* p; if ((rc = dev_alloc(c, c->field_allocs, &p, N))) return rc; S.d_charges = p; c->field_allocs.pop_back(); }
     c->x_begin = 0; c->x_end = N;

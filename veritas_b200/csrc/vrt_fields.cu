@@ -127,51 +127,127 @@ __device__ double block_excl_scan(double v, double* sh, double* total) {
     return sh[w] + (inc - v);
 }
 
-__global__ void __launch_bounds__(PT) k_poisson(VrtFields F) {
+// Five small multi-CTA passes (tiles of PTILE entries, PTHR threads, PEL consecutive entries per thread; every cross-tile
+// quantity is a fixed-order sum of per-tile partials that each CTA recomputes for itself, so there are no atomics and the
+// result does not depend on scheduling — all ranks of a multi-GPU run get the same bits):
+//   k_poisson_rhs   b = (rho + rho_neutral) dx^2/eps0, tile sums            (EMSolver.cpp:160-166)
+//   k_poisson_conv  b' = b - sum(b) e_0,  z = T^-1 b', tile sums
+//   k_poisson_scan1 c = inclusive prefix of z, tile sums
+//   k_poisson_dsum  tile sums of d = mean(c) - c
+//   k_poisson_scan2 PHI_0 = sum(b), PHI_i = sum_{k<i} d_k
+constexpr int PTHR = 256, PEL = 4, PTILE = PTHR * PEL;
+constexpr int PMAXT = 4096;      // tiles: N <= 4 Mi finest cells
+
+// sum of part[0..G) (returned to all threads) and, for this CTA, of part[0..blk): thread t owns a contiguous run of partials
+__device__ double partial_prefix(const double* part, int G, int blk, double* sh, double* total) {
+    __shared__ double own;
+    const int cp = (G + PTHR - 1) / PTHR, lo = threadIdx.x * cp, hi = min(G, lo + cp);
+    double loc = 0.0, before = 0.0;
+    for (int k = lo; k < hi; k++) { if (k == blk) before = loc; loc += part[k]; }
+    const double off = block_excl_scan(loc, sh, total);
+    if (blk >= lo && blk < hi) own = off + before;
+    __syncthreads();
+    return own;
+}
+
+__global__ void __launch_bounds__(PTHR) k_poisson_rhs(VrtFields F, double* part) {
+    __shared__ double sh[40];
+    const int N = F.N, i0 = blockIdx.x * PTILE + threadIdx.x * PEL;
+    const double te = VRT_EPS0_INV, w = F.dx * F.dx;
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < PEL; k++) {
+        const int i = i0 + k;
+        if (i < N) { double v = te * (F.charge[i] + F.neutral[i]); v *= w; F.scratch[i] = v; s += v; }
+    }
+    const double t = block_sum(s, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(PTHR) k_poisson_conv(VrtFields F, const double* part_b, double* part_z, int G) {
     __shared__ double sh[40];
     __shared__ double green[PK + 1];
-    const int N = F.N, tid = threadIdx.x;
-    double* b = F.scratch;          // rhs, then b'
-    double* z = F.scratch + N;      // T^-1 b'
-    double* cpre = F.scratch + 2L * N;
+    __shared__ double tile[PTILE + 2 * PK];
+    const int N = F.N, tid = threadIdx.x, t0 = blockIdx.x * PTILE;
+    const double* b = F.scratch;
+    double* z = F.scratch + N;
     if (tid <= PK) {
         const double rho = 1.0 / (7.0 + sqrt(48.0)), Cg = 6.0 / sqrt(48.0);   // rho = 7 - sqrt(48) without cancellation
         double g = Cg;
         for (int k = 0; k < tid; k++) g *= rho;
         green[tid] = g;
     }
-    const double te = VRT_EPS0_INV, w = F.dx * F.dx;
-    const int per = (N + PT - 1) / PT, lo = tid * per, hi = min(N, lo + per);
-    double s = 0.0;
-    for (int i = lo; i < hi; i++) { double v = te * (F.charge[i] + F.neutral[i]); v *= w; b[i] = v; s += v; }
-    const double sb = block_sum(s, sh);
-    if (tid == 0) b[0] -= sb;
-    __syncthreads();
-    // z = T^-1 b'  (strided so that neighbouring threads read neighbouring entries)
-    for (int i = tid; i < N; i += PT) {
-        double acc = green[0] * b[i];
-        for (int k = 1; k <= PK; k++) {
-            int ip = (i + k) % N;
-            int im = (((i - k) % N) + N) % N;
-            acc += green[k] * (b[ip] + b[im]);
-        }
-        z[i] = acc;
+    double sb;
+    partial_prefix(part_b, G, 0, sh, &sb);
+    for (int e = tid; e < PTILE + 2 * PK; e += PTHR) {
+        int i = t0 - PK + e;                       // periodic wrap (N may be smaller than the halo)
+        while (i < 0) i += N;
+        while (i >= N) i -= N;
+        const double v = b[i];
+        tile[e] = (i == 0) ? v - sb : v;
     }
     __syncthreads();
-    // c_i = inclusive prefix of z
-    double loc = 0.0;
-    for (int i = lo; i < hi; i++) loc += z[i];
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < PEL; k++) {
+        const int e = tid * PEL + k + PK, i = t0 + tid * PEL + k;
+        if (i < N) {
+            double acc = green[0] * tile[e];
+            for (int d = 1; d <= PK; d++) acc += green[d] * (tile[e + d] + tile[e - d]);
+            z[i] = acc; s += acc;
+        }
+    }
+    const double t = block_sum(s, sh);
+    if (tid == 0) part_z[blockIdx.x] = t;
+    if (blockIdx.x == 0 && tid == 0) F.scratch[3L * N] = sb;
+}
+
+__global__ void __launch_bounds__(PTHR) k_poisson_scan1(VrtFields F, const double* part_z, double* part_c, int G) {
+    __shared__ double sh[40];
+    const int N = F.N, tid = threadIdx.x, i0 = blockIdx.x * PTILE + tid * PEL;
+    const double* z = F.scratch + N;
+    double* cpre = F.scratch + 2L * N;
     double tot;
-    double off = block_excl_scan(loc, sh, &tot);
-    double run = off, csum = 0.0;
-    for (int i = lo; i < hi; i++) { run += z[i]; cpre[i] = run; csum += run; }
-    const double cmean = block_sum(csum, sh) / (double)N;
-    // y_i = sum_{k<i} (cmean - c_k)
-    loc = 0.0;
-    for (int i = lo; i < hi; i++) loc += (cmean - cpre[i]);
-    off = block_excl_scan(loc, sh, &tot);
-    run = off;
-    for (int i = lo; i < hi; i++) { double d = cmean - cpre[i]; F.PHI[i] = (i == 0) ? sb : run; run += d; }
+    const double base = partial_prefix(part_z, G, blockIdx.x, sh, &tot);
+    double v[PEL], loc = 0.0;
+#pragma unroll
+    for (int k = 0; k < PEL; k++) { v[k] = (i0 + k < N) ? z[i0 + k] : 0.0; loc += v[k]; }
+    double run = base + block_excl_scan(loc, sh, &tot), csum = 0.0;
+#pragma unroll
+    for (int k = 0; k < PEL; k++) if (i0 + k < N) { run += v[k]; cpre[i0 + k] = run; csum += run; }
+    const double t = block_sum(csum, sh);
+    if (tid == 0) part_c[blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(PTHR) k_poisson_dsum(VrtFields F, const double* part_c, double* part_d, int G) {
+    __shared__ double sh[40];
+    const int N = F.N, tid = threadIdx.x, i0 = blockIdx.x * PTILE + tid * PEL;
+    const double* cpre = F.scratch + 2L * N;
+    double csum;
+    partial_prefix(part_c, G, 0, sh, &csum);
+    const double cmean = csum / (double)N;
+    double loc = 0.0;
+#pragma unroll
+    for (int k = 0; k < PEL; k++) if (i0 + k < N) loc += (cmean - cpre[i0 + k]);
+    const double t = block_sum(loc, sh);
+    if (tid == 0) part_d[blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(PTHR) k_poisson_scan2(VrtFields F, const double* part_c, const double* part_d, int G) {
+    __shared__ double sh[40];
+    const int N = F.N, tid = threadIdx.x, i0 = blockIdx.x * PTILE + tid * PEL;
+    const double* cpre = F.scratch + 2L * N;
+    double csum, tot;
+    partial_prefix(part_c, G, 0, sh, &csum);
+    const double cmean = csum / (double)N;
+    const double base = partial_prefix(part_d, G, blockIdx.x, sh, &tot);
+    double d[PEL], loc = 0.0;
+#pragma unroll
+    for (int k = 0; k < PEL; k++) { d[k] = (i0 + k < N) ? (cmean - cpre[i0 + k]) : 0.0; loc += d[k]; }
+    double run = base + block_excl_scan(loc, sh, &tot);
+    const double sb = F.scratch[3L * N];
+#pragma unroll
+    for (int k = 0; k < PEL; k++) if (i0 + k < N) { F.PHI[i0 + k] = (i0 + k == 0) ? sb : run; run += d[k]; }
 }
 
 // EMFieldSolver::GetEfield without the Ex0 term (EMSolver.cpp:137-154)
@@ -268,7 +344,15 @@ int vrt_fields_rhs_update_faces(vrt_ctx* c, int step, const VrtStepParams* d_par
 
 int vrt_fields_poisson(vrt_ctx* c) {
     VrtFields& F = c->F;
-    k_poisson<<<1, PT, 0, c->stream>>>(F);
+    const int G = (F.N + PTILE - 1) / PTILE;
+    if (G > PMAXT) { c->err = "vrt_poisson: x_size_finest too large for the tiled solver"; return VRT_ERR_ARG; }
+    double* part = F.scratch + 3L * F.N + 8;      // 4 arrays of PMAXT tile partials behind the three N-vectors and sum(b)
+    k_poisson_rhs<<<G, PTHR, 0, c->stream>>>(F, part);
+    k_poisson_conv<<<G, PTHR, 0, c->stream>>>(F, part, part + PMAXT, G);
+    k_poisson_scan1<<<G, PTHR, 0, c->stream>>>(F, part + PMAXT, part + 2 * PMAXT, G);
+    k_poisson_dsum<<<G, PTHR, 0, c->stream>>>(F, part + 2 * PMAXT, part + 3 * PMAXT, G);
+    k_poisson_scan2<<<G, PTHR, 0, c->stream>>>(F, part + 2 * PMAXT, part + 3 * PMAXT, G);
+    c->launches += 4;
     k_efield<<<grid1(F.N + 2 * F.epad), 256, 0, c->stream>>>(F, 1);
     k_commit_ex0<<<1, 1, 0, c->stream>>>(F);
     c->launches += 3;

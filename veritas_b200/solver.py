@@ -18,6 +18,7 @@ DESC_KEYS = ("depth", "x_pos", "p_pos", "n_x", "n_p", "up", "down", "left", "rig
 
 M_E = 9.10938291e-31      # veritas.cpp:16
 Q_E = 1.60217657e-19      # veritas.cpp:17
+EPS0_INV = 1.1294e+11      # veritas.hpp:22 (literal)
 CS = 299792458.0          # veritas.hpp:26
 
 
@@ -249,9 +250,12 @@ class LaserPlasmaRun:
         return min(self.cfl * self.ctx.cfl_bound(), self.dt_max)
 
     def run_fields_phase(self):
-        """veritas.cpp:135-144: fields-only while t <= 3T with dt = T/400."""
-        dt, t, n = self.dt_max, self.dt_max, 0
+        """veritas.cpp:135-144: fields-only while t <= 3T.  The reference's driver uses the fixed dt = T/400 there, which is
+        only stable while c dt/dx < ~1 (nx <~ 4000 for its 10-wavelength box); like its plasma phase, this driver bounds the
+        step by SolverManager::CalculateDt so that fine meshes (config 3: c T/400 = 16 dx) stay finite."""
+        t, n = self.dt_max, 0
         while not (t > 3 * self.T):
+            dt = self.calculate_dt()
             self.advance_fields(dt)
             t += dt
             n += 1
