@@ -208,15 +208,16 @@ int vrt_set_hierarchy(vrt_ctx* c, int s, int n_patches, const vrt_patch_desc* d)
         L.plane = (long)(L.n_x + 2 * L.gx) * L.pitch + 1024;   // slack: the last strip's bulk load may run past the last column
         if (!check(c, L.plane < (1L << 31), "vrt_set_hierarchy: slab plane exceeds 2^31 cells (split the domain over more GPUs)")) return VRT_ERR_ARG;
         L.dx = c->F.dx; L.dp = sp.dp_finest;
-        for (int k = 0; k < 3; k++) if ((rc = dev_alloc(c, S.allocations, &L.f[k], L.plane))) return rc;
-        for (int k = 0; k < 5; k++) {
-            if ((rc = dev_alloc(c, S.allocations, &L.FxH[k], L.plane))) return rc;
-            if ((rc = dev_alloc(c, S.allocations, &L.FpH[k], L.plane))) return rc;
-        }
+        // two pooled allocations (uniform plane stride): each is one 3-D tensor {p, column, plane} for the TMA descriptors
+        double *fpool, *hpool;
+        if ((rc = dev_alloc(c, S.allocations, &fpool, 3 * (size_t)L.plane))) return rc;
+        if ((rc = dev_alloc(c, S.allocations, &hpool, 10 * (size_t)L.plane))) return rc;
+        for (int k = 0; k < 3; k++) L.f[k] = fpool + k * L.plane;
+        for (int k = 0; k < 5; k++) { L.FxH[k] = hpool + (2 * k) * L.plane; L.FpH[k] = hpool + (2 * k + 1) * L.plane; }
         if ((rc = dev_alloc(c, S.allocations, &L.chargeR, L.n_x))) return rc;
         if ((rc = dev_alloc(c, S.allocations, &L.currentR, L.n_x))) return rc;
         S.i_f0 = S.i_f1 = 0;
-        return 0;
+        return vrt_fused_make_maps(c, s);
     }
     // split path: SoA planes per patch, reference layout
     S.level_patches.assign(c->max_depth + 1, {});

@@ -99,9 +99,12 @@ struct VrtSlabDev {
     long plane;                  // doubles per plane = (n_x + 2*gx) * pitch
     double dx, dp;
     double* f[3];                // rotating: cur0 = f^n, cur1 = stage value, spare
-    double* FxH[5]; double* FpH[5];
+    double* FxH[5]; double* FpH[5];   // one allocation, planes interleaved FxH[0], FpH[0], FxH[1], ... (one 3-D TMA box covers a stage's history)
     double *chargeR, *currentR;  // n_x each
 };
+// TMA descriptors (CUtensorMap, 128 bytes each) of a slab's planes for the fused stage: [0] the three f planes with a
+// one-column box, [S] (S = 1..5) the interleaved flux history with a box of 2S planes
+struct alignas(64) VrtSlabMaps { unsigned char m[6][128]; int W; };
 
 struct VrtSpeciesState {
     VrtSpecies sp;
@@ -115,6 +118,7 @@ struct VrtSpeciesState {
     std::vector<int> table_order;        // table index -> caller's patch number
     VrtPatchDev* d_patches = nullptr;    // device copy of `table`
     std::vector<double*> allocations;
+    VrtSlabMaps maps;
     void* conn_pool = nullptr;           // device pool holding the connectivity tables of all patches
     bool has_amr = false;                // any nested cell / coarse-fine face / same-level neighbour
     std::vector<std::vector<int>> level_patches;   // table indices per depth (contiguous ranges)
@@ -182,3 +186,4 @@ int vrt_fields_neutralize(vrt_ctx* c);
 int vrt_fused_stage(vrt_ctx* c, int s, const double* d_dt, int step);
 int vrt_fused_moments(vrt_ctx* c, int s);
 int vrt_fused_zero_ghosts(vrt_ctx* c, int s, int plane_idx);
+int vrt_fused_make_maps(vrt_ctx* c, int s);
