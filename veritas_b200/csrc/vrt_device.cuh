@@ -74,13 +74,14 @@ __device__ __forceinline__ double weno_fast(double f1, double f2, double f3, dou
     const double mm = 1.0e-10;
     const double DL = (mm + bL) * (mm + bL), DR = (mm + bR) * (mm + bR);
     const double S = DL + DR;
-    const int e = min((__double2hiint(S) >> 20) & 0x7ff, 2045);
-    const double sc = __hiloint2double((2046 - e) << 20, 0);
+    // sc = 2^(1023 - exponent(S)): S > 0 and finite (D ~ f^4 stays far below 2^1023 for any f the reference itself survives)
+    const double sc = __hiloint2double(0x7fe00000 - (__double2hiint(S) & 0x7ff00000), 0);
     const double dl = DL * sc, dr = DR * sc, ss = dl + dr;
     const double h = 0.75 * ss;
     const double NL = dr * fma(ss, fma(-0.5, dr, h), dr * dr);
     const double NR = dl * fma(ss, fma(-0.5, dl, h), dl * dl);
-    const bool pickL = right ? (NL > NR) : (NL < NR);
+    // right: the larger weight, left: the smaller one; on a tie both candidates are equal
+    const bool pickL = (NL > NR) == right;
     const double a = (pickL ? NL : NR) * rcp_scaled(NL + NR);
     return a * fL + (1 - a) * fR;
 }
