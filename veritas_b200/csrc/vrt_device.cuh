@@ -64,13 +64,8 @@ __device__ __forceinline__ double rcp_scaled(double d) {
 //   NL = DR (0.75 S^2 + DR^2 - 0.5 DR S),  NR likewise with DL;   W/(wL0+wR0) = sel(NL,NR)/(NL+NR)
 // DL, DR are first scaled by the power of two that brings S = DL+DR into [1,2) (exact), so S^3 cannot overflow.
 // Differs from the reference's evaluation order by a few ulp of the weights (continuous; SURVEY.md H2 allows it).
-__device__ __forceinline__ double weno_fast(double f1, double f2, double f3, double f4, bool right) {
-    const double fL = (1.0 / 6) * (-f1 + 5 * f2 + 2 * f3);
-    const double fR = (1.0 / 6) * (2 * f2 + 5 * f3 - f4);
-    const double AL = f1 - 2 * f2 + f3, BL = f3 - f1;
-    const double AR = f2 - 2 * f3 + f4, BR = f4 - f2;
-    const double bL = 4.0 / 3 * (AL * AL) + 0.5 * AL * BL + 0.25 * (BL * BL);
-    const double bR = 4.0 / 3 * (AR * AR) - 0.5 * AR * BR + 0.25 * (BR * BR);
+// common tail: candidates fL, fR and smoothness indicators bL, bR -> face value
+__device__ __forceinline__ double weno_fast_tail(double fL, double fR, double bL, double bR, bool right) {
     const double mm = 1.0e-10;
     const double DL = (mm + bL) * (mm + bL), DR = (mm + bR) * (mm + bR);
     const double S = DL + DR;
@@ -84,4 +79,26 @@ __device__ __forceinline__ double weno_fast(double f1, double f2, double f3, dou
     const bool pickL = (NL > NR) == right;
     const double a = (pickL ? NL : NR) * rcp_scaled(NL + NR);
     return a * fL + (1 - a) * fR;
+}
+__device__ __forceinline__ double weno_fast(double f1, double f2, double f3, double f4, bool right) {
+    const double fL = (1.0 / 6) * (-f1 + 5 * f2 + 2 * f3);
+    const double fR = (1.0 / 6) * (2 * f2 + 5 * f3 - f4);
+    const double AL = f1 - 2 * f2 + f3, BL = f3 - f1;
+    const double AR = f2 - 2 * f3 + f4, BR = f4 - f2;
+    const double bL = 4.0 / 3 * (AL * AL) + 0.5 * AL * BL + 0.25 * (BL * BL);
+    const double bR = 4.0 / 3 * (AR * AR) - 0.5 * AR * BR + 0.25 * (BR * BR);
+    return weno_fast_tail(fL, fR, bL, bR, right);
+}
+// The same for a stencil that slides by one cell per call (the x direction of the marching kernel): the right candidate's
+// second difference A and first difference B are the left candidate's of the next face, and the two smoothness indicators
+// differ only in the sign of the cross term, so each call forms one (A, B) pair, bR = t1 - t2, and hands bL = t1 + t2 of the
+// next face on through `bL_next` (in: this face's bL from the previous call).
+__device__ __forceinline__ double weno_fast_sliding(double f1, double f2, double f3, double f4, bool right, double& bL_next) {
+    const double fL = (1.0 / 6) * (-f1 + 5 * f2 + 2 * f3);
+    const double fR = (1.0 / 6) * (2 * f2 + 5 * f3 - f4);
+    const double AR = f2 - 2 * f3 + f4, BR = f4 - f2;
+    const double t1 = fma(0.25 * BR, BR, 4.0 / 3 * (AR * AR)), t2 = (0.5 * AR) * BR;
+    const double bL = bL_next, bR = t1 - t2;
+    bL_next = t1 + t2;
+    return weno_fast_tail(fL, fR, bL, bR, right);
 }
