@@ -49,15 +49,13 @@ __device__ __forceinline__ double weno(double f1, double f2, double f3, double f
 
 
 // ---- fused-path arithmetic helpers ---------------------------------------------------------------------------
-// reciprocal of a well-scaled operand (no denormal / inf / nan): MUFU.RCP64H seed + two Newton steps (< 1 ulp)
+// reciprocal of a well-scaled operand (no denormal / inf / nan): MUFU.RCP64H seed (relative error e0 < 2^-20) and one
+// third-order step x (1 + e + e^2), e = 1 - d x: error e0^3 plus rounding, < 1 ulp, in three fp64 instructions
 __device__ __forceinline__ double rcp_scaled(double d) {
     double x;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
-    double e = fma(-d, x, 1.0);
-    x = fma(x, e, x);
-    e = fma(-d, x, 1.0);
-    x = fma(x, e, x);
-    return x;
+    const double e = fma(-d, x, 1.0);
+    return fma(x, fma(e, e, e), x);
 }
 // Rectangle::GetWenoEdgeValueNoMax (Rectangle.cpp:980-1030) with the five divisions folded into one.
 //   wL = oL/(oL+oR) = DR/(DL+DR),  D = (1e-10+b)^2;   wL0 = wL(0.75+wL(wL-0.5))  =>  wL0 (DL+DR)^3 = NL
@@ -65,7 +63,8 @@ __device__ __forceinline__ double rcp_scaled(double d) {
 // DL, DR are first scaled by the power of two that brings S = DL+DR into [1,2) (exact), so S^3 cannot overflow.
 // Differs from the reference's evaluation order by a few ulp of the weights (continuous; SURVEY.md H2 allows it).
 // common tail: candidates fL, fR and smoothness indicators bL, bR -> face value
-__device__ __forceinline__ double weno_fast_tail(double fL, double fR, double bL, double bR, bool right) {
+// fLmR = fL - fR
+__device__ __forceinline__ double weno_fast_tail(double fLmR, double fR, double bL, double bR, bool right) {
     const double mm = 1.0e-10;
     const double DL = (mm + bL) * (mm + bL), DR = (mm + bR) * (mm + bR);
     const double S = DL + DR;
@@ -78,16 +77,15 @@ __device__ __forceinline__ double weno_fast_tail(double fL, double fR, double bL
     // right: the larger weight, left: the smaller one; on a tie both candidates are equal
     const bool pickL = (NL > NR) == right;
     const double a = (pickL ? NL : NR) * rcp_scaled(NL + NR);
-    return a * fL + (1 - a) * fR;
+    return fma(a, fLmR, fR);                     // a fL + (1 - a) fR
 }
 __device__ __forceinline__ double weno_fast(double f1, double f2, double f3, double f4, bool right) {
-    const double fL = (1.0 / 6) * (-f1 + 5 * f2 + 2 * f3);
     const double fR = (1.0 / 6) * (2 * f2 + 5 * f3 - f4);
     const double AL = f1 - 2 * f2 + f3, BL = f3 - f1;
     const double AR = f2 - 2 * f3 + f4, BR = f4 - f2;
     const double bL = 4.0 / 3 * (AL * AL) + 0.5 * AL * BL + 0.25 * (BL * BL);
     const double bR = 4.0 / 3 * (AR * AR) - 0.5 * AR * BR + 0.25 * (BR * BR);
-    return weno_fast_tail(fL, fR, bL, bR, right);
+    return weno_fast_tail((1.0 / 6) * (AR - AL), fR, bL, bR, right);      // fL - fR = (f4 - 3 f3 + 3 f2 - f1) / 6 = (AR - AL) / 6
 }
 // The same for a stencil that slides by one cell per call (the x direction of the marching kernel): the right candidate's
 // second difference A and first difference B are the left candidate's of the next face, and the two smoothness indicators
@@ -100,5 +98,5 @@ __device__ __forceinline__ double weno_fast_sliding(double f1, double f2, double
     const double t1 = fma(0.25 * BR, BR, 4.0 / 3 * (AR * AR)), t2 = (0.5 * AR) * BR;
     const double bL = bL_next, bR = t1 - t2;
     bL_next = t1 + t2;
-    return weno_fast_tail(fL, fR, bL, bR, right);
+    return weno_fast_tail(fL - fR, fR, bL, bR, right);
 }
