@@ -99,6 +99,9 @@ int vrt_destroy(vrt_ctx* c) {
     for (double* p : c->field_allocs) cudaFree(p);
     if (c->d_params) cudaFree(c->d_params);
     if (c->d_comm) cudaFree(c->d_comm);
+    for (cudaStream_t st : c->aux_stream) if (st) cudaStreamDestroy(st);
+    for (cudaEvent_t ev : c->aux_join) if (ev) cudaEventDestroy(ev);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -580,6 +583,40 @@ double vrt_update_time(double time, int step, double dt) {   // Settings::Update
     return time;
 }
 
+// Mesh::Advance of every species for one RK stage (SolverManager.cpp:33-35).  The species do not interact inside a stage, so
+// species s > 0 is enqueued on its own stream between a fork and a join event: concurrent branches of the step graph.  This
+// halves the launch-latency-bound time of small and AMR hierarchies and fills the tail of the last wave of large kernels.
+static int vlasov_stages_all(vrt_ctx* c, int i) {
+    int r;
+    const bool fork = c->fork_species && c->n_ranks == 1 && c->n_species > 1;
+    if (!fork) {
+        for (int s = 0; s < c->n_species; s++) if ((r = vlasov_stage_impl(c, s, &c->d_params->dt, i))) return r;
+        return 0;
+    }
+    if (!c->ev_fork) {
+        VRT_CUDA(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        c->aux_stream.resize(c->n_species - 1); c->aux_join.resize(c->n_species - 1);
+        for (int s = 1; s < c->n_species; s++) {
+            VRT_CUDA(c, cudaStreamCreateWithFlags(&c->aux_stream[s - 1], cudaStreamNonBlocking));
+            VRT_CUDA(c, cudaEventCreateWithFlags(&c->aux_join[s - 1], cudaEventDisableTiming));
+        }
+    }
+    cudaStream_t main_stream = c->stream;
+    VRT_CUDA(c, cudaEventRecord(c->ev_fork, main_stream));
+    for (int s = 1; s < c->n_species; s++) {
+        cudaStream_t aux = c->aux_stream[s - 1];
+        VRT_CUDA(c, cudaStreamWaitEvent(aux, c->ev_fork, 0));
+        c->stream = aux;
+        r = vlasov_stage_impl(c, s, &c->d_params->dt, i);
+        c->stream = main_stream;
+        if (r) return r;
+        VRT_CUDA(c, cudaEventRecord(c->aux_join[s - 1], aux));
+    }
+    if ((r = vlasov_stage_impl(c, 0, &c->d_params->dt, i))) return r;
+    for (int s = 1; s < c->n_species; s++) VRT_CUDA(c, cudaStreamWaitEvent(main_stream, c->aux_join[s - 1], 0));
+    return 0;
+}
+
 // the six stages of SolverManager::Advance as stream work (SolverManager.cpp:28-39)
 static int enqueue_step(vrt_ctx* c) {
     int r;
@@ -587,7 +624,7 @@ static int enqueue_step(vrt_ctx* c) {
         if ((r = moments_impl(c))) return r;
         if ((r = vrt_fields_poisson(c))) return r;
         if (i == 0 && (r = vrt_fields_snapshot_stage0(c))) return r;
-        for (int s = 0; s < c->n_species; s++) if ((r = vlasov_stage_impl(c, s, &c->d_params->dt, i))) return r;
+        if ((r = vlasov_stages_all(c, i))) return r;
         if ((r = vrt_fields_rhs_update_faces(c, i, c->d_params))) return r;
     }
     return 0;
@@ -648,6 +685,7 @@ long vrt_last_step_launches(const vrt_ctx* c) { return c ? c->last_step_launches
 int vrt_set_option(vrt_ctx* c, int option, int value) {
     if (!c) return VRT_ERR_ARG;
     if (option == 0) { c->use_graph = value != 0; return 0; }
+    if (option == 1) { c->fork_species = value != 0; drop_graphs(c); return 0; }
     return VRT_ERR_ARG;
 }
 
