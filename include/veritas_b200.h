@@ -68,6 +68,16 @@ int vrt_set_species(vrt_ctx* ctx, int s, double mass, double charge, double pmin
 int vrt_set_hierarchy(vrt_ctx* ctx, int s, int n_patches, const vrt_patch_desc* patches);
 int vrt_set_path(vrt_ctx* ctx, int path);
 int vrt_get_path(vrt_ctx* ctx, int s);
+/* Regrid without the host round trip.  Mesh::promoteHierarchyToMesh(false) (Mesh.cpp:794-875):
+ * replaces the hierarchy of species s (split path) by `patches` and fills the new patches from the old ones on the device —
+ * Mesh::InterMeshDataTransfer (Mesh.cpp:116-130): GetDataFromCoarseLevelRectangle (Rectangle.cpp:892-918),
+ * GetDataFromSameLevelRectangle (920-941), GetDataFromCoarseNewLevelRectangle (1100-1128), states 0 and 1.  Cells no
+ * old or new coarser patch reaches stay 0, as in the reference.  Follow with vrt_push_data and vrt_commit_state. */
+int vrt_regrid(vrt_ctx* ctx, int s, int n_patches, const vrt_patch_desc* patches);
+/* Rectangle::ErrorEstimate(i, j) > refinementCriteria (Rectangle.hpp:128-130, errorWeights of Rectangle.cpp:68-74) for the
+ * n_x x n_p interior cells of a patch (p fast), one byte per cell.  Rectangle::getError (Rectangle.cpp:866-890) applies its
+ * margins and ORs Settings::RefinementOverride on the host. */
+int vrt_error_flags(vrt_ctx* ctx, int s, int patch, const double weights[5], double criteria, unsigned char* flags_host);
 
 /* ---- data movement (init, regrid, output) --------------------------------------------------- */
 /* state: 0 = f^n, 1 = current stage value, 2 = low-order predictor (Rectangle.hpp:96-98). */

@@ -22,16 +22,20 @@ REF = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 HOST = os.path.join(ROOT, "oracle", "_ref", "host_harness")
 
 
-def run_both(tmp_path, args):
+def run_both(tmp_path, args, host_env=None):
     outs = {}
     for name, exe in (("ref", REF), ("host", HOST)):
         if not os.path.exists(exe):
             pytest.fail(f"{exe} missing: run __graft_entry__.build() in the build container")
         path = str(tmp_path / f"{name}.bin")
         env = dict(os.environ, OPENBLAS_NUM_THREADS="1")
+        if name == "host" and host_env:
+            env.update(host_env)
         r = subprocess.run([exe, path] + args, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
         assert r.returncode == 0, r.stdout[-2000:]
         outs[name] = read_dump(path)
+        outs[name + "_log"] = r.stdout
+    run_both.host_log = outs["host_log"]
     return outs["ref"], outs["host"]
 
 
@@ -72,10 +76,25 @@ def test_host_layer_single_level_fused(tmp_path):
     print("single level, 4 free-running steps: worst relative L2", {k: "%.2e" % v for k, v in worst.items()})
 
 
-def test_host_layer_amr_with_regrid(tmp_path):
-    """Lfinest = 3, regrid every 2 steps (BASELINE config 4 shape): initial hierarchy construction, error flagging, clustering,
-    old->new data transfer on the host; all numerics on the GPU."""
-    ref, host = run_both(tmp_path, ["48", "32", "3", "0.5", "9", "pre_steps=1600", "regrid_every=2", "threads=4"])
+@pytest.mark.parametrize("regrid_data_path", ["device", "host"])
+def test_host_layer_amr_with_regrid(tmp_path, regrid_data_path):
+    """Lfinest = 3, regrid every 2 steps (BASELINE config 4 shape): initial hierarchy construction, error flagging, clustering
+    on the host; all numerics on the GPU.  The regrid data path — Rectangle::ErrorEstimate and Mesh::InterMeshDataTransfer —
+    runs on the device (vrt_error_flags, vrt_regrid; default) or, with VRT_HOST_REGRID=1, on the host mirrors; either way the
+    hierarchies after every regrid must be the reference's and f must agree."""
+    ref, host = run_both(tmp_path, ["48", "32", "3", "0.5", "9", "pre_steps=1600", "regrid_every=2", "threads=4"],
+                         host_env={"VRT_HOST_REGRID": "1" if regrid_data_path == "host" else "0", "VRT_TRACE": "1"})
     worst, most = compare(ref, host, 9, 1e-10, 1e-12)
     assert most >= 4
-    print("3 levels, regrid every 2 steps, 9 free-running steps: worst relative L2", {k: "%.2e" % v for k, v in worst.items()}, "max patches/level", most)
+    # 4 regrids x 2 species went through the device movers (or none of them)
+    assert run_both.host_log.count("vrt_regrid: species") == (8 if regrid_data_path == "device" else 0), run_both.host_log[-1500:]
+    print(f"3 levels, regrid every 2 steps ({regrid_data_path} data path), 9 free-running steps: worst relative L2",
+          {k: "%.2e" % v for k, v in worst.items()}, "max patches/level", most)
+
+
+def test_host_layer_two_level_tail_regrid(tmp_path):
+    """Lfinest = 2 with the refinement forced into the high-momentum tail (BASELINE config 2 shape), regrid every 3 steps on
+    the device data path."""
+    ref, host = run_both(tmp_path, ["64", "48", "2", "0.3", "7", "pre_steps=1700", "refine_mode=1", "tail_p0=1", "regrid_every=3", "threads=4"])
+    worst, most = compare(ref, host, 7, 1e-10, 1e-12)
+    print("2 levels (tail), regrid every 3 steps, 7 free-running steps: worst relative L2", {k: "%.2e" % v for k, v in worst.items()}, "max patches/level", most)

@@ -2,6 +2,8 @@
 #include "vrt_internal.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
 
@@ -14,6 +16,7 @@ int vrt_fields_init_tables(vrt_ctx* c);
 int vrt_split_init_tables(vrt_ctx* c);
 
 static std::string g_err;
+extern "C" { static int ready_species(vrt_ctx* c, int s); }
 
 namespace {
 
@@ -172,6 +175,53 @@ int vrt_set_slab(vrt_ctx* c, int rank, int n_ranks, int x_begin, int x_end) {
     return 0;
 }
 
+// split path storage of one species: SoA planes per patch in the reference's padded layout, the device patch table grouped
+// by depth, and the connectivity tables (S must hold no storage; S.desc is set by the caller)
+static int build_split(vrt_ctx* c, int s, int n_patches, const vrt_patch_desc* d) {
+    VrtSpeciesState& S = c->S[s];
+    const VrtSpecies sp = S.sp;
+    const int r = c->refinement_ratio;
+    int rc;
+    S.level_patches.assign(c->max_depth + 1, {});
+    std::vector<int> order(n_patches);
+    for (int p = 0; p < n_patches; p++) order[p] = p;
+    // the device table is grouped by depth so that one level is a contiguous range; S.patches is indexed by
+    // the caller's patch number, table_index maps it into the table
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return d[a].depth < d[b].depth; });
+    vrt_conn conn;
+    if (vrt_conn_derive(conn, n_patches, d, r, c->max_depth)) { c->err = "vrt_set_hierarchy: " + conn.err; return VRT_ERR_ARG; }
+    S.patches.resize(n_patches);
+    std::vector<VrtPatchDev> table(n_patches);
+    S.table_index.assign(n_patches, 0);
+    S.table_order = order;
+    for (int ti = 0; ti < n_patches; ti++) {
+        const int p = order[ti];
+        const vrt_patch_desc& q = d[p];
+        VrtPatchDev P{};
+        P.n_x = q.n_x; P.n_p = q.n_p; P.x_pos = q.x_pos; P.p_pos = q.p_pos;
+        P.up = q.up; P.down = q.down; P.left = q.left; P.right = q.right; P.depth = q.depth;
+        P.rtb = (int)std::lround(std::pow((double)r, q.depth));
+        P.pitch = q.n_p + 4; P.npad = (long)(q.n_x + 4) * (q.n_p + 4);
+        P.dx = std::pow((double)r, (double)q.depth) * c->F.dx;              // Settings::GetDx (Settings.cpp:142-144)
+        P.dp = std::pow((double)r, (double)q.depth) * sp.dp_finest;         // Settings::GetDp (Settings.cpp:138-140)
+        double** planes[] = {&P.f0, &P.f1, &P.f2, &P.fx, &P.fp, &P.ex, &P.ep, &P.FxL, &P.FpL, &P.FxLS, &P.FpLS, &P.FxDS, &P.FpDS, &P.Rp, &P.Rm, &P.Cx, &P.Cp};
+        for (double** pl : planes) if ((rc = dev_alloc(c, S.allocations, pl, P.npad))) return rc;
+        if ((rc = dev_alloc(c, S.allocations, &P.FxH, 6 * P.npad))) return rc;
+        if ((rc = dev_alloc(c, S.allocations, &P.FpH, 6 * P.npad))) return rc;
+        if ((rc = dev_alloc(c, S.allocations, &P.chargeR, (long)P.n_x * P.rtb))) return rc;
+        if ((rc = dev_alloc(c, S.allocations, &P.currentR, (long)P.n_x * P.rtb))) return rc;
+        S.patches[p] = P; table[ti] = P; S.table_index[p] = ti;
+        S.level_patches[q.depth].push_back(ti);
+    }
+    S.table = table;
+    if ((rc = vrt_amr_upload_connectivity(c, s, conn))) return rc;
+    VRT_CUDA(c, cudaMalloc(&S.d_patches, sizeof(VrtPatchDev) * n_patches));
+    VRT_CUDA(c, cudaMemcpyAsync(S.d_patches, S.table.data(), sizeof(VrtPatchDev) * n_patches, cudaMemcpyHostToDevice, c->stream));
+    VRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+
 int vrt_set_hierarchy(vrt_ctx* c, int s, int n_patches, const vrt_patch_desc* d) {
     if (!c) return VRT_ERR_ARG;
     if (!check(c, c->grid_set && s >= 0 && s < c->n_species && c->S[s].configured, "vrt_set_hierarchy: set grid and species first")) return VRT_ERR_STATE;
@@ -222,44 +272,55 @@ int vrt_set_hierarchy(vrt_ctx* c, int s, int n_patches, const vrt_patch_desc* d)
         S.i_f0 = S.i_f1 = 0;
         return vrt_fused_make_maps(c, s);
     }
-    // split path: SoA planes per patch, reference layout
-    S.level_patches.assign(c->max_depth + 1, {});
-    std::vector<int> order(n_patches);
-    for (int p = 0; p < n_patches; p++) order[p] = p;
-    // the device table is grouped by depth so that one level is a contiguous range; S.patches is indexed by
-    // the caller's patch number, table_index maps it into the table
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return d[a].depth < d[b].depth; });
-    vrt_conn conn;
-    if (vrt_conn_derive(conn, n_patches, d, r, c->max_depth)) { c->err = "vrt_set_hierarchy: " + conn.err; return VRT_ERR_ARG; }
-    S.patches.resize(n_patches);
-    std::vector<VrtPatchDev> table(n_patches);
-    S.table_index.assign(n_patches, 0);
-    S.table_order = order;
-    for (int ti = 0; ti < n_patches; ti++) {
-        const int p = order[ti];
+    return build_split(c, s, n_patches, d);
+}
+
+// Mesh::promoteHierarchyToMesh(false) without the host round trip: the new hierarchy's storage is
+// built while the old one is still resident, Mesh::InterMeshDataTransfer (Mesh.cpp:116-130) runs as kernels between the two
+// device patch tables, then the old storage is released.  The caller continues as after vrt_set_hierarchy + uploads:
+// vrt_push_data, vrt_commit_state.
+int vrt_regrid(vrt_ctx* c, int s, int n_patches, const vrt_patch_desc* d) {
+    if (!c) return VRT_ERR_ARG;
+    if (!check(c, c->grid_set && s >= 0 && s < c->n_species && c->S[s].configured && !c->S[s].desc.empty(), "vrt_regrid: no hierarchy to regrid")) return VRT_ERR_STATE;
+    if (!check(c, n_patches >= 1 && d, "vrt_regrid: bad arguments")) return VRT_ERR_ARG;
+    VrtSpeciesState& S = c->S[s];
+    if (!check(c, S.path == VRT_PATH_SPLIT && c->max_depth >= 1, "vrt_regrid: only hierarchies on the split path regrid")) return VRT_ERR_STATE;
+    const int r = c->refinement_ratio;
+    for (int p = 0; p < n_patches; p++) {
         const vrt_patch_desc& q = d[p];
-        VrtPatchDev P{};
-        P.n_x = q.n_x; P.n_p = q.n_p; P.x_pos = q.x_pos; P.p_pos = q.p_pos;
-        P.up = q.up; P.down = q.down; P.left = q.left; P.right = q.right; P.depth = q.depth;
-        P.rtb = (int)std::lround(std::pow((double)r, q.depth));
-        P.pitch = q.n_p + 4; P.npad = (long)(q.n_x + 4) * (q.n_p + 4);
-        P.dx = std::pow((double)r, (double)q.depth) * c->F.dx;              // Settings::GetDx (Settings.cpp:142-144)
-        P.dp = std::pow((double)r, (double)q.depth) * sp.dp_finest;         // Settings::GetDp (Settings.cpp:138-140)
-        double** planes[] = {&P.f0, &P.f1, &P.f2, &P.fx, &P.fp, &P.ex, &P.ep, &P.FxL, &P.FpL, &P.FxLS, &P.FpLS, &P.FxDS, &P.FpDS, &P.Rp, &P.Rm, &P.Cx, &P.Cp};
-        for (double** pl : planes) if ((rc = dev_alloc(c, S.allocations, pl, P.npad))) return rc;
-        if ((rc = dev_alloc(c, S.allocations, &P.FxH, 6 * P.npad))) return rc;
-        if ((rc = dev_alloc(c, S.allocations, &P.FpH, 6 * P.npad))) return rc;
-        if ((rc = dev_alloc(c, S.allocations, &P.chargeR, (long)P.n_x * P.rtb))) return rc;
-        if ((rc = dev_alloc(c, S.allocations, &P.currentR, (long)P.n_x * P.rtb))) return rc;
-        S.patches[p] = P; table[ti] = P; S.table_index[p] = ti;
-        S.level_patches[q.depth].push_back(ti);
+        if (!check(c, q.depth >= 0 && q.depth <= c->max_depth && q.n_x >= r && q.n_p >= r && q.n_x % r == 0 && q.n_p % r == 0,
+                   "vrt_regrid: bad patch descriptor")) return VRT_ERR_ARG;
     }
-    S.table = table;
-    if ((rc = vrt_amr_upload_connectivity(c, s, conn))) return rc;
-    VRT_CUDA(c, cudaMalloc(&S.d_patches, sizeof(VrtPatchDev) * n_patches));
-    VRT_CUDA(c, cudaMemcpyAsync(S.d_patches, S.table.data(), sizeof(VrtPatchDev) * n_patches, cudaMemcpyHostToDevice, c->stream));
+    cudaSetDevice(c->device);
     VRT_CUDA(c, cudaStreamSynchronize(c->stream));
-    return 0;
+    drop_graphs(c);
+    // park the old storage
+    VrtSpeciesState old;
+    old.allocations.swap(S.allocations); old.patches.swap(S.patches); old.table.swap(S.table); old.table_index.swap(S.table_index);
+    old.table_order.swap(S.table_order); old.level_patches.swap(S.level_patches); old.desc.swap(S.desc);
+    old.d_patches = S.d_patches; S.d_patches = nullptr;
+    old.conn_pool = S.conn_pool; S.conn_pool = nullptr;
+    S.has_amr = false;
+    S.desc.assign(d, d + n_patches);
+    int rc = build_split(c, s, n_patches, d);
+    const long l0 = c->launches;
+    if (!rc) rc = vrt_amr_transfer(c, old, S);
+    if (getenv("VRT_TRACE")) fprintf(stderr, "vrt_regrid: species %d, %zu -> %d patches, %ld transfer kernels on the device\n", s, old.desc.size(), n_patches, c->launches - l0);
+    if (!rc) { cudaError_t e = cudaStreamSynchronize(c->stream); if (e != cudaSuccess) { c->err = std::string("vrt_regrid: ") + cudaGetErrorString(e); rc = VRT_ERR_CUDA; } }
+    for (double* p : old.allocations) cudaFree(p);
+    if (old.d_patches) cudaFree(old.d_patches);
+    if (old.conn_pool) cudaFree(old.conn_pool);
+    return rc;
+}
+
+// Rectangle::ErrorEstimate (Rectangle.hpp:128-130) > refinementCriteria for every interior cell of a patch, as a byte map
+// (n_x x n_p, p fast); the caller applies the margins of Rectangle::getError (Rectangle.cpp:866-890) and ORs the user's
+// RefinementOverride.  1 byte per cell crosses the bus instead of the 16 bytes of the two f states.
+int vrt_error_flags(vrt_ctx* c, int s, int patch, const double weights[5], double criteria, unsigned char* flags_host) {
+    if (int r = ready_species(c, s)) return r;
+    if (!check(c, weights && flags_host && patch >= 0 && patch < (int)c->S[s].desc.size(), "vrt_error_flags: bad arguments")) return VRT_ERR_ARG;
+    if (!check(c, c->S[s].path == VRT_PATH_SPLIT, "vrt_error_flags: split path only")) return VRT_ERR_STATE;
+    return vrt_amr_error_flags(c, s, patch, weights, criteria, flags_host);
 }
 
 // ---- data movement ----------------------------------------------------------------------------------

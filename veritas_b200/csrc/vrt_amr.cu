@@ -212,6 +212,84 @@ __device__ void coarse_level_values(const VrtPatchDev& Q, int r, int i, int j, i
     else for (int k = 0; k < r; k++) { out[2 * k] = ip[r * (r - 1) + k]; out[2 * k + 1] = ip[r * (r - 2) + k]; }
 }
 
+// the same interpolation, all r x r sub-cells of the coarse cell under fine cell (i, j): ip[k * r + l] = sub-cell (x k, p l)
+// (GetWenoValueFromCoarseLevel with d = -1, used by the regrid data transfer)
+__device__ void coarse_level_block(const VrtPatchDev& Q, int r, int i, int j, int val, double* ip) {
+    const double* f = fstate(Q, val);
+    const int ic = i / r - Q.x_pos, jc = j / r - Q.p_pos;
+    double temps[5][RMAX], part[RMAX], sum = 0.0;
+    for (int k = -2; k < 3; k++)
+        interpolants_ref(r, f[NS(Q, ic - 2, jc + k)], f[NS(Q, ic - 1, jc + k)], f[NS(Q, ic, jc + k)], f[NS(Q, ic + 1, jc + k)], f[NS(Q, ic + 2, jc + k)], temps[k + 2]);
+    for (int k = 0; k < r; k++) {
+        interpolants_ref(r, temps[0][k], temps[1][k], temps[2][k], temps[3][k], temps[4][k], part);
+        for (int l = 0; l < r; l++) { ip[k * r + l] = part[l]; sum += part[l]; }
+    }
+    const double correction = f[NS(Q, ic, jc)] - 1.0 / (double)(r * r) * sum;
+    for (int k = 0; k < r * r; k++) ip[k] += correction;
+}
+
+// ---- regrid data movers: Mesh::InterMeshDataTransfer (Mesh.cpp:116-130) ---------------------------
+// `dst` = patches of one level of the NEW hierarchy (blockIdx.y), `src` = the n_src patches of one level of the old (or, for
+// the last pass, new) hierarchy.  marks = Rectangle::is_interpolated of the new patches, one byte per padded cell, at
+// mark_off[table index].
+// Rectangle::GetDataFromSameLevelRectangle (Rectangle.cpp:920-941): every padded cell of the target that lies in the interior
+// of a source patch of the same level takes its state-1 value (states 0 and 1), and is marked.  Source patches of a level are
+// disjoint, so at most one matches.
+__global__ void k_xfer_same(const VrtPatchDev* dst, int dst0, const VrtPatchDev* src, int n_src, unsigned char* marks, const long* mark_off) {
+    const VrtPatchDev& P = dst[blockIdx.y];
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.npad) return;
+    const int gi = P.x_pos + (int)(c / P.pitch) - 2, gj = P.p_pos + (int)(c % P.pitch) - 2;
+    for (int q = 0; q < n_src; q++) {
+        const VrtPatchDev& Q = src[q];
+        if (gi >= Q.x_pos && gi < Q.x_pos + Q.n_x && gj >= Q.p_pos && gj < Q.p_pos + Q.n_p) {
+            const double v = Q.f1[NS(Q, gi - Q.x_pos, gj - Q.p_pos)];
+            P.f0[c] = v; P.f1[c] = v;
+            marks[mark_off[dst0 + blockIdx.y] + c] = 1;
+            return;
+        }
+    }
+}
+// Rectangle::GetDataFromCoarseLevelRectangle (Rectangle.cpp:892-918; only_unmarked = 0, marks the cells it writes) and
+// Rectangle::GetDataFromCoarseNewLevelRectangle (Rectangle.cpp:1100-1128; only_unmarked = 1: skips coarse cells whose
+// sub-cell (1,1) already holds old data, does not mark): one thread per coarse cell under the target plus one ring.
+__global__ void k_xfer_coarse(const VrtPatchDev* dst, int dst0, const VrtPatchDev* src, int n_src, int r, int only_unmarked,
+                              unsigned char* marks, const long* mark_off) {
+    const VrtPatchDev& P = dst[blockIdx.y];
+    const int tx = P.x_pos / r, tp = P.p_pos / r, tnx = P.n_x / r, tnp = P.n_p / r;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long)(tnx + 2) * (tnp + 2)) return;
+    const int ci = tx - 1 + (int)(t / (tnp + 2)), cj = tp - 1 + (int)(t % (tnp + 2));
+    unsigned char* mk = marks + mark_off[dst0 + blockIdx.y];
+    for (int q = 0; q < n_src; q++) {
+        const VrtPatchDev& Q = src[q];
+        if (ci >= Q.x_pos && ci < Q.x_pos + Q.n_x && cj >= Q.p_pos && cj < Q.p_pos + Q.n_p) {
+            if (only_unmarked && mk[NS(P, r * (ci - tx) + 1, r * (cj - tp) + 1)]) return;
+            double ip[RMAX * RMAX];
+            coarse_level_block(Q, r, r * ci + 1, r * cj + 1, 1, ip);
+            for (int k = 0; k < r; k++)
+                for (int l = 0; l < r; l++) {
+                    const long cell = NS(P, (ci - tx) * r + k, (cj - tp) * r + l);
+                    P.f0[cell] = ip[l + r * k]; P.f1[cell] = ip[l + r * k];
+                    if (!only_unmarked) mk[cell] = 1;
+                }
+            return;
+        }
+    }
+}
+// Rectangle::ErrorEstimate (Rectangle.hpp:128-130) on state 1, compared with the refinement criterion
+struct ErrW { double w[5]; };
+__global__ void k_error_flags(const VrtPatchDev* all, int patch, ErrW W, double criteria, unsigned char* out) {
+    const VrtPatchDev& P = all[patch];
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long)P.n_x * P.n_p) return;
+    const int i = (int)(t / P.n_p), j = (int)(t % P.n_p);
+    const double* f = P.f1;
+    const double c = f[NS(P, i, j)], xp = f[NS(P, i + 1, j)], xm = f[NS(P, i - 1, j)], pp = f[NS(P, i, j + 1)], pm = f[NS(P, i, j - 1)];
+    const double e = W.w[0] * fabs(xp - xm) + W.w[1] * fabs(pp - pm) + W.w[2] * fabs(xp - 2 * c + xm) + W.w[3] * fabs(pp - 2 * c + pm) + W.w[4] * fabs(c);
+    out[t] = e > criteria ? 1 : 0;
+}
+
 // ---- K3: same-level ghost copy, side strips only (corners belong to k_corners / k_ghost_coarse) ---------------------
 // thread t: [0, 2 n_p) cells of the xm / xp sides, [2 n_p, 2 n_p + 2 n_x) cells of the pm / pp sides; both ghost layers
 __global__ void k_ghost_same(const VrtPatchDev* level, const VrtPatchDev* all, int val, int r) {
@@ -572,5 +650,66 @@ int vrt_amr_level_boundary_fluxes(vrt_ctx* c, int s, int depth, int step) {
         S.d_patches + S.level_patches[depth][0], S.d_patches, step, c->refinement_ratio, make_sp(S.sp), c->F);
     c->launches += 1;
     VRT_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+// Mesh::InterMeshDataTransfer (Mesh.cpp:116-130) between the old and the new device patch tables of one species
+int vrt_amr_transfer(vrt_ctx* c, const VrtSpeciesState& O, VrtSpeciesState& N) {
+    const int r = c->refinement_ratio, nl = (int)N.level_patches.size();
+    if (r > RMAX) { c->err = "vrt_regrid: refinement ratio too large"; return VRT_ERR_ARG; }
+    // Rectangle::is_interpolated of the new patches
+    std::vector<long> off(N.table.size() + 1, 0);
+    for (size_t k = 0; k < N.table.size(); k++) off[k + 1] = off[k] + N.table[k].npad;
+    unsigned char* marks = nullptr; long* d_off = nullptr;
+    VRT_CUDA(c, cudaMalloc(&marks, std::max<long>(off.back(), 1)));
+    VRT_CUDA(c, cudaMalloc(&d_off, sizeof(long) * off.size()));
+    VRT_CUDA(c, cudaMemsetAsync(marks, 0, std::max<long>(off.back(), 1), c->stream));
+    VRT_CUDA(c, cudaMemcpyAsync(d_off, off.data(), sizeof(long) * off.size(), cudaMemcpyHostToDevice, c->stream));
+    auto level_of = [](const VrtSpeciesState& S, int l, const VrtPatchDev** first, int* n) {
+        *n = (l >= 0 && l < (int)S.level_patches.size()) ? (int)S.level_patches[l].size() : 0;
+        *first = *n ? S.d_patches + S.level_patches[l][0] : nullptr;
+    };
+    auto same = [&](int l) {          // new level l <- old level l
+        const VrtPatchDev *dst, *src; int nd, ns;
+        level_of(N, l, &dst, &nd); level_of(O, l, &src, &ns);
+        if (!nd || !ns) return;
+        long npad = 0;
+        for (int p : N.level_patches[l]) npad = std::max(npad, N.table[p].npad);
+        k_xfer_same<<<dim3(blocks(npad, 256), nd), 256, 0, c->stream>>>(dst, N.level_patches[l][0], src, ns, marks, d_off);
+        c->launches += 1;
+    };
+    auto coarse = [&](int l, const VrtSpeciesState& Src, int only_unmarked) {      // new level l <- level l + 1 of Src
+        const VrtPatchDev *dst, *src; int nd, ns;
+        level_of(N, l, &dst, &nd); level_of(Src, l + 1, &src, &ns);
+        if (!nd || !ns) return;
+        long cells = 0;
+        for (int p : N.level_patches[l]) cells = std::max(cells, (long)(N.table[p].n_x / r + 2) * (N.table[p].n_p / r + 2));
+        k_xfer_coarse<<<dim3(blocks(cells, 128), nd), 128, 0, c->stream>>>(dst, N.level_patches[l][0], src, ns, r, only_unmarked, marks, d_off);
+        c->launches += 1;
+    };
+    for (int l = 0; l + 1 < nl; l++) { coarse(l, O, 0); same(l); }
+    if (nl > 1) same(nl - 1);
+    for (int l = nl - 1; l > 0; l--) coarse(l - 1, N, 1);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(marks); cudaFree(d_off);
+    if (e != cudaSuccess) { c->err = std::string("vrt_regrid transfer: ") + cudaGetErrorString(e); return VRT_ERR_CUDA; }
+    return 0;
+}
+
+int vrt_amr_error_flags(vrt_ctx* c, int s, int patch, const double weights[5], double criteria, unsigned char* flags_host) {
+    VrtSpeciesState& S = c->S[s];
+    const VrtPatchDev& P = S.patches[patch];
+    const long n = (long)P.n_x * P.n_p;
+    unsigned char* d = nullptr;
+    VRT_CUDA(c, cudaMalloc(&d, n));
+    ErrW W; for (int k = 0; k < 5; k++) W.w[k] = weights[k];
+    k_error_flags<<<blocks(n, 256), 256, 0, c->stream>>>(S.d_patches, S.table_index[patch], W, criteria, d);
+    c->launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(flags_host, d, n, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) { c->err = std::string("vrt_error_flags: ") + cudaGetErrorString(e); return VRT_ERR_CUDA; }
     return 0;
 }

@@ -179,6 +179,8 @@ int vrt_amr_level_pass(vrt_ctx* c, int s, int depth, int type, int val);
 int vrt_amr_push_data(vrt_ctx* c, int s, int val);
 int vrt_amr_push_boundary_c(vrt_ctx* c, int s);
 int vrt_amr_level_boundary_fluxes(vrt_ctx* c, int s, int depth, int step);
+int vrt_amr_transfer(vrt_ctx* c, const VrtSpeciesState& old_state, VrtSpeciesState& new_state);
+int vrt_amr_error_flags(vrt_ctx* c, int s, int patch, const double weights[5], double criteria, unsigned char* flags_host);
 // 1-D solver (vrt_fields.cu, compiled with -fmad=false)
 int vrt_fields_rhs_update_faces(vrt_ctx* c, int step, const VrtStepParams* d_params);
 int vrt_fields_poisson(vrt_ctx* c);

@@ -182,11 +182,20 @@ void Rectangle::getError(std::vector<coords>& flaggedCells, int particleType) {
     margin *= 3;
     const int lo_x = std::max(x_pos, margin), hi_x = std::min(x_pos + n_x, settings_->GetXSize(depth) - margin);
     const int lo_p = std::max(p_pos, margin), hi_p = std::min(p_pos + n_p, settings_->GetPSize(depth, particleType) - margin);
+    // the estimate is evaluated where the data live: on the device (one byte per cell comes back) or on the host mirror
+    std::vector<unsigned char> dev;
+    if (device_flags_) {
+        dev.resize((size_t)n_x * n_p);
+        settings_->Check(vrt_error_flags(settings_->Gpu(), particleType, patch_id, errorWeights.data(), settings_->refinementCriteria, dev.data()),
+                         "vrt_error_flags");
+    }
     for (int i = lo_x; i < hi_x; i++)
-        for (int j = lo_p; j < hi_p; j++)
-            if ((ErrorEstimate(i - x_pos, j - p_pos) > settings_->refinementCriteria) ||
-                settings_->RefinementOverride((i + 0.5) * dx, Momentum(j - p_pos), depth, particleType))
+        for (int j = lo_p; j < hi_p; j++) {
+            const bool over = device_flags_ ? dev[(size_t)(i - x_pos) * n_p + (j - p_pos)] != 0
+                                            : ErrorEstimate(i - x_pos, j - p_pos) > settings_->refinementCriteria;
+            if (over || settings_->RefinementOverride((i + 0.5) * dx, Momentum(j - p_pos), depth, particleType))
                 flaggedCells.push_back(std::make_pair(i, j));
+        }
 }
 
 // Rectangle::GetInterpolantsREF (Rectangle.cpp:121-137)
@@ -376,7 +385,7 @@ void Mesh::SyncHost() {
 // Mesh::getError (Mesh.cpp:212-295).  init: the analytic pre-flagging; with MKLINIT == 0 its result is discarded (quirk Q6).
 void Mesh::getError(const int& lvl, bool init, std::vector<coords>& flaggedCells) {
     if (init) return;
-    for (auto& r : levels.at(settings.maxDepth - lvl)->rectangles) r->getError(flaggedCells, particleType);
+    for (auto& r : levels.at(settings.maxDepth - lvl)->rectangles) { r->device_flags_ = device_current_ && device_regrid_; r->getError(flaggedCells, particleType); }
 }
 
 void Mesh::getExtrema(rect& extrema, const std::vector<coords>& flaggedCells) {      // bounding box of the flags (Mesh.cpp:625-642)
@@ -533,7 +542,10 @@ void Mesh::mergeDownFlaggedData(const int& lvl, const rect& r, std::vector<coord
 // level; flags of level l are united with the footprint of the level-(l+2) patches so that nesting survives
 void Mesh::updateHierarchy(bool init) {
     if (hierarchy.empty()) { std::cerr << "Exception Occured: hierarchy is empty, cannot update it." << std::endl; exit(EXIT_FAILURE); }
-    SyncHost();
+    // VRT_HOST_REGRID=1 keeps the reference's host-side regrid data path (download, Rectangle::getError and
+    // InterMeshDataTransfer on the mirrors, upload); default: error flags and old -> new transfer run on the device
+    device_regrid_ = !(getenv("VRT_HOST_REGRID") && atoi(getenv("VRT_HOST_REGRID")));
+    if (!device_regrid_) SyncHost();
     std::vector<coords> flagged, own, below, tmp;
     const int top = (int)hierarchy.size() - 1;
     for (int l = top; l > -1; l--) {
@@ -584,6 +596,10 @@ void Mesh::InterMeshDataTransfer(const std::vector<std::unique_ptr<Level>>& old_
 // there), f -> vrt_patch_upload_f, PushData, FCTTimeStep(0,-1,3) -> vrt_commit_state
 void Mesh::promoteHierarchyToMesh(bool init) {
     const int N = (int)hierarchy.size() - 1, empty = settings.maxDepth - N;
+    vrt_ctx* g = settings.Gpu();
+    const bool on_device = !init && device_regrid_ && device_current_ && settings.maxDepth >= 1 &&
+                           vrt_get_path(g, particleType) == VRT_PATH_SPLIT;
+    if (!init && !on_device) SyncHost();          // the host transfer below reads the old rectangles' mirrors
     std::vector<std::unique_ptr<Level>> old_levels;
     if (!init) for (auto& lvl : levels) old_levels.push_back(std::move(lvl));
     levels.clear();
@@ -598,27 +614,29 @@ void Mesh::promoteHierarchyToMesh(bool init) {
                 r.second.first - r.first.first, r.second.second - r.first.second, r.first.first, r.first.second, depth, settings, bc,
                 r.second.second == pmax, r.first.second == 0, r.first.first == 0, r.second.first == xmax, particleType));
     }
-    if (init) for (auto& lvl : levels) for (auto& r : lvl->rectangles) r->InitializeDistribution();
-    if (!init) InterMeshDataTransfer(old_levels);
-
-    vrt_ctx* g = settings.Gpu();
     std::vector<vrt_patch_desc> desc;
     int id = 0;
     for (auto& lvl : levels) for (auto& r : lvl->rectangles) { r->patch_id = id++; desc.push_back(r->Descriptor()); }
-    // AMR hierarchies run on the split path; a single full-domain patch takes the fused streaming path
-    settings.Check(vrt_set_hierarchy(g, particleType, (int)desc.size(), desc.data()), "vrt_set_hierarchy");
-    const bool fused = vrt_get_path(g, particleType) == VRT_PATH_FUSED;
-    std::vector<double> plane;
-    for (auto& lvl : levels)
-        for (auto& r : lvl->rectangles) {
-            const size_t npad = (size_t)(r->n_x + 4) * (r->n_p + 4);
-            plane.resize(npad);
-            for (int state = 0; state < 2; state++) {
-                for (size_t c = 0; c < npad; c++) plane[c] = r->f[3 * c + state];
-                settings.Check(vrt_patch_upload_f(g, particleType, r->patch_id, state, plane.data()), "vrt_patch_upload_f");
+    if (on_device) {
+        // InterMeshDataTransfer between the old and the new device patch tables; Rectangle::f of the new patches is a stale
+        // mirror until the next SyncHost()
+        settings.Check(vrt_regrid(g, particleType, (int)desc.size(), desc.data()), "vrt_regrid");
+    } else {
+        if (init) for (auto& lvl : levels) for (auto& r : lvl->rectangles) r->InitializeDistribution();
+        if (!init) InterMeshDataTransfer(old_levels);
+        // AMR hierarchies run on the split path; a single full-domain patch takes the fused streaming path
+        settings.Check(vrt_set_hierarchy(g, particleType, (int)desc.size(), desc.data()), "vrt_set_hierarchy");
+        std::vector<double> plane;
+        for (auto& lvl : levels)
+            for (auto& r : lvl->rectangles) {
+                const size_t npad = (size_t)(r->n_x + 4) * (r->n_p + 4);
+                plane.resize(npad);
+                for (int state = 0; state < 2; state++) {
+                    for (size_t c = 0; c < npad; c++) plane[c] = r->f[3 * c + state];
+                    settings.Check(vrt_patch_upload_f(g, particleType, r->patch_id, state, plane.data()), "vrt_patch_upload_f");
+                }
             }
-        }
-    (void)fused;
+    }
     PushData();
     settings.Check(vrt_commit_state(g, particleType), "vrt_commit_state");
     device_current_ = true;

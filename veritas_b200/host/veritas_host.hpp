@@ -138,6 +138,7 @@ public:
     double relativeToBottom;
     std::vector<double> f, chargeR, energyR, currentR;     // f: 3 states per padded cell, AoS (Rectangle.hpp:96-98)
     int patch_id = -1;                                      // number of this patch in vrt_set_hierarchy
+    bool device_flags_ = false;                             // getError evaluates ErrorEstimate on the device (vrt_error_flags)
 
     Rectangle(int n_x, int n_p, int x_pos, int p_pos, int depth, Settings& settings, const std::shared_ptr<Rectangle>& bc,
               bool up, bool down, bool left, bool right, int particleType);
@@ -187,6 +188,7 @@ class Mesh {
     std::shared_ptr<EMFieldSolver> EMSolver;
     std::shared_ptr<Rectangle> bc;
     bool device_current_ = false;      // the device holds newer data than Rectangle::f
+    bool device_regrid_ = true;        // regrid data path on the device (vrt_error_flags, vrt_regrid) instead of the host mirrors
 public:
     int particleType;
     std::vector<std::unique_ptr<Level>> levels;
