@@ -287,6 +287,17 @@ def main():
                 "per_stage_GBps": per_stage, "peak_source": peak_src,
                 "stage_cell_updates_per_s": round(6 * cells_loc / (tot_ms * 1e-3), 1)}
     breakdown["fused_stage"] = round(2 * tot_ms, 3)     # both species
+    # DRAM traffic of one launch of the stage kernel from the committed ncu --set full capture (same workload only), next to
+    # the algorithmic bytes of that launch
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "fused_traffic.json")))
+        if wl == "c3" and n_gpus == 1:
+            roofline["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            roofline["traffic_unit"] = f"bytes per launch of stage {tr['stage']} (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
+            roofline["traffic_algorithmic"] = float(stage_bytes(cells_loc, tr["stage"]))
+            roofline["traffic_source"] = tr["source"]
+    except Exception:
+        pass
     run_steps = args.warmup + 2 * args.steps + reps
 
     # ---- sanity of the state the numbers were measured on ---------------------------------------------------------------

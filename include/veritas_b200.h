@@ -139,6 +139,13 @@ int vrt_set_option(vrt_ctx* ctx, int option, int value);
  * with r^(depth+quadrature_depth) points per direction; writes states 0 and 1.  SURVEY.md §8(f) item 2. */
 int vrt_init_maxwellian_slab(vrt_ctx* ctx, int s, double xl, double xr, double n0, double T, int quadrature_depth);
 
+/* ---- checkpoint / restart (no counterpart in the reference) ---------------------------- */
+/* Binary image of the context at a step boundary: hierarchy and f of every species, the 1-D field arrays, PHI, Ex0, the
+ * neutralisation charge and the time.  vrt_checkpoint_read needs a context with the same vrt_set_grid (and vrt_set_slab /
+ * vrt_set_path) calls; it recreates the hierarchies itself.  A restarted run continues bit for bit.  One file per rank. */
+int vrt_checkpoint_write(vrt_ctx* ctx, const char* path);
+int vrt_checkpoint_read(vrt_ctx* ctx, const char* path);
+
 /* ---- hierarchy connectivity on the host (no device needed) ---------------------------------------- */
 /* The tables Rectangle::CalculateConnectivitySame / CalculateConnectivityFromFiner build (Rectangle.cpp:671-864), as
  * vrt_set_hierarchy derives them.  side: 0 xm, 1 xp (n_p/r + 2 strips, first and last = the 2-cell corners), 2 pm, 3 pp

@@ -15,7 +15,8 @@
 //
 // usage: ref_harness out.bin nx np Lfinest density steps [key=value ...]
 //   keys: dump_every=1 stage_dumps=0 regrid_every=0 threads=N refine_mode=0 tail_p0=2 pre_steps=-1
-//         time_only=0 internals=0 a0=1
+//         time_only=0 internals=0 a0=1 file_output=0 (every N steps: SolverManager::fileOutput + OutputRectangles into
+//         ./output, which must exist with its rectangleData subdirectory) precision=15
 #include "veritas.hpp"
 #include "Settings.hpp"
 #include "SolverManager.hpp"
@@ -121,7 +122,8 @@ int main(int argc, char** argv) {
     int steps = atoi(argv[6]);
     std::map<std::string, double> kv = {{"dump_every", 1}, {"stage_dumps", 0}, {"regrid_every", 0}, {"threads", 0},
                                         {"refine_mode", 0}, {"tail_p0", 2}, {"pre_steps", -1}, {"time_only", 0},
-                                        {"internals", 0}, {"a0", 1}, {"np_ion", 0}};
+                                        {"internals", 0}, {"a0", 1}, {"np_ion", 0},
+                                        {"file_output", 0}, {"precision", 15}};
     for (int i = 7; i < argc; i++) {
         std::string a = argv[i]; size_t e = a.find('=');
         if (e == std::string::npos || !kv.count(a.substr(0, e))) { fprintf(stderr, "bad arg %s\n", argv[i]); return 2; }
@@ -144,6 +146,11 @@ int main(int argc, char** argv) {
     particles.np = {np, np_ion};
     particles.dp = {0.1, 0.1};
     particles.pmin = {0.1, 0.1};
+    const int file_output = (int)kv["file_output"];
+    output.precision = (int)kv["precision"];
+    output.energy = false;      // dN/dp: diagnostic with a data race in the reference, not reproduced
+    if (!file_output) output.time = output.rectangleData = output.charge = output.potential = output.EFieldLongitudinal =
+        output.EFieldTransverse = output.BFieldTransverse = output.AFieldSquared = false;
 
     Settings settings(grid, particles, output);
     SolverManager SM(settings);
@@ -208,6 +215,7 @@ int main(int argc, char** argv) {
             if (counter >= regrid_every - 1) { SM.reGrid(t); counter = 0; cells = count_cells(); } else counter++;
         }
         t += dt_adaptive;
+        if (file_output > 0 && n % file_output == 0) { SM.fileOutput(t); SM.OutputRectangles(t); }
         if (!time_only && (n % dump_every == 0 || n == steps)) {
             put1("step" + std::to_string(n) + "/dt", dt_adaptive);
             dump_state(SM, settings, "step" + std::to_string(n), internals);

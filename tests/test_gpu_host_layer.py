@@ -98,3 +98,41 @@ def test_host_layer_two_level_tail_regrid(tmp_path):
     ref, host = run_both(tmp_path, ["64", "48", "2", "0.3", "7", "pre_steps=1700", "refine_mode=1", "tail_p0=1", "regrid_every=3", "threads=4"])
     worst, most = compare(ref, host, 7, 1e-10, 1e-12)
     print("2 levels (tail), regrid every 3 steps, 7 free-running steps: worst relative L2", {k: "%.2e" % v for k, v in worst.items()}, "max patches/level", most)
+
+
+def _tokens(path):
+    return [line.split() for line in open(path).read().splitlines()]
+
+
+def test_host_layer_text_output_formats(tmp_path):
+    """SURVEY.md §8(f) item 3: SolverManager::fileOutput / OutputRectangles of the host classes write the reference's files
+    (EMSolver.cpp:340-477, Mesh.cpp:877-902) from the device mirrors: same file set and names (the time stamp is part of
+    the rectangleData names), same line / token structure, integers identical, numbers equal to the printed precision up to the
+    round-off the two solvers differ by."""
+    args = ["48", "32", "3", "0.5", "4", "pre_steps=1600", "regrid_every=2", "threads=4", "file_output=2", "precision=8"]
+    files = {}
+    for name, exe in (("ref", REF), ("host", HOST)):
+        cwd = tmp_path / name
+        (cwd / "output" / "rectangleData").mkdir(parents=True)
+        r = subprocess.run([exe, str(cwd / "dump.bin")] + args, cwd=str(cwd), env=dict(os.environ, OPENBLAS_NUM_THREADS="1"),
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:]
+        files[name] = sorted(str(p.relative_to(cwd)) for p in (cwd / "output").rglob("*.txt"))
+    assert files["ref"] == files["host"] and len(files["ref"]) >= 8 + 6, files
+    for rel in files["ref"]:
+        a, b = _tokens(tmp_path / "host" / rel), _tokens(tmp_path / "ref" / rel)
+        assert len(a) == len(b) and [len(x) for x in a] == [len(x) for x in b], rel
+        if "rectangleData" in rel:
+            scale = max(abs(float(t[2])) for t in b if t[0] != "r")
+            for la, lb in zip(a, b):
+                if lb[0] == "r":
+                    assert la == lb, rel
+                else:
+                    assert la[:2] == lb[:2], rel
+                    assert abs(float(la[2]) - float(lb[2])) <= 2e-4 * abs(float(lb[2])) + 1e-12 * scale, (rel, la, lb)
+        else:
+            va = np.array([float(t) for line in a for t in line]); vb = np.array([float(t) for line in b for t in line])
+            tol = 1e-6 if ("potential" in rel or "EFieldLong" in rel) else 1e-7      # E_x / PHI: SURVEY.md H0
+            assert rel_l2(va, vb) < tol, (rel, rel_l2(va, vb))
+            if "time" in rel or "Trans" in rel or "ASquared" in rel:
+                assert open(tmp_path / "host" / rel).read() == open(tmp_path / "ref" / rel).read(), rel      # byte for byte

@@ -24,6 +24,7 @@ UNITS = [
     ("vrt_fused.cu", []),
     ("vrt_init.cu", []),
     ("vrt_comm.cu", []),
+    ("vrt_checkpoint.cu", []),
 ]
 HOST_UNITS = ["case_abi.cpp"]
 

@@ -74,6 +74,17 @@ class Context:
     def set_path(self, path):
         self.call("vrt_set_path", path)
 
+    def checkpoint_write(self, path):
+        self.call("vrt_checkpoint_write", str(path).encode())
+
+    def checkpoint_read(self, path, patches=None):
+        """patches[s] = descriptors of the stored hierarchy (only needed by this harness's upload/download shape checks;
+        the library recreates the hierarchy from the file)."""
+        self.call("vrt_checkpoint_read", str(path).encode())
+        if patches is not None:
+            for s, ps in enumerate(patches):
+                self.patches[s] = [{k: p[k] for k in DESC_KEYS} for p in ps]
+
     def get_path(self, s):
         return self.L.vrt_get_path(self.h, s)
 
