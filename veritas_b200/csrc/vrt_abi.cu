@@ -571,14 +571,14 @@ static int vlasov_stage_impl(vrt_ctx* c, int s, const double* d_dt, int step) {
         if (c->n_ranks > 1 && (r = vrt_comm_halo_exchange(c, s))) return r;
         return 0;
     }
-    const int nl = (int)S.level_patches.size();
-    for (int d = nl - 1; d >= 0; d--) if ((r = vrt_split_substep(c, s, d, d_dt, step, 0))) return r;
+    // Mesh::Advance (Mesh.cpp:64-89); each sub-step serves all levels in one launch (vrt_split_substep_all)
+    if ((r = vrt_split_substep_all(c, s, d_dt, step, 0))) return r;
     if ((r = push_data_impl(c, s, 2))) return r;
-    for (int d = nl - 1; d >= 0; d--) if ((r = vrt_split_substep(c, s, d, d_dt, step, 1))) return r;
+    if ((r = vrt_split_substep_all(c, s, d_dt, step, 1))) return r;
     if ((r = vrt_amr_push_boundary_c(c, s))) return r;
-    for (int d = nl - 1; d >= 0; d--) if ((r = vrt_split_substep(c, s, d, d_dt, step, 2))) return r;
+    if ((r = vrt_split_substep_all(c, s, d_dt, step, 2))) return r;
     if ((r = push_data_impl(c, s, 1))) return r;
-    if (step == 5) for (int d = nl - 1; d >= 0; d--) if ((r = vrt_split_substep(c, s, d, d_dt, step, 3))) return r;
+    if (step == 5 && (r = vrt_split_substep_all(c, s, d_dt, step, 3))) return r;
     return 0;
 }
 

@@ -653,6 +653,22 @@ int vrt_amr_level_boundary_fluxes(vrt_ctx* c, int s, int depth, int step) {
     return 0;
 }
 
+// the same for every coarse level in one launch: the table is grouped by depth (finest first), so the patches of depth >= 1
+// are its tail; patches without a finer level carry no flagged faces and fall through
+int vrt_amr_level_boundary_fluxes_all(vrt_ctx* c, int s, int step) {
+    VrtSpeciesState& S = c->S[s];
+    int first = -1;
+    long m = 0;
+    for (size_t d = 1; d < S.level_patches.size(); d++)
+        for (int p : S.level_patches[d]) { if (first < 0) first = p; m = std::max(m, S.table[p].npad); }
+    if (first < 0 || !S.has_amr) return 0;
+    k_level_boundary_fluxes<<<dim3(blocks(m, 128), (unsigned)(S.table.size() - first)), 128, 0, c->stream>>>(
+        S.d_patches + first, S.d_patches, step, c->refinement_ratio, make_sp(S.sp), c->F);
+    c->launches += 1;
+    VRT_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
 // Mesh::InterMeshDataTransfer (Mesh.cpp:116-130) between the old and the new device patch tables of one species
 int vrt_amr_transfer(vrt_ctx* c, const VrtSpeciesState& O, VrtSpeciesState& N) {
     const int r = c->refinement_ratio, nl = (int)N.level_patches.size();

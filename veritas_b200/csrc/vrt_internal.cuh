@@ -172,6 +172,7 @@ struct vrt_ctx {
 // ---- launchers implemented in the kernel translation units -----------------------------------------
 // split path (vrt_split.cu, compiled with -fmad=false)
 int vrt_split_substep(vrt_ctx* c, int s, int depth, const double* d_dt, int step, int substep);
+int vrt_split_substep_all(vrt_ctx* c, int s, const double* d_dt, int step, int substep);
 int vrt_split_moments(vrt_ctx* c, int s);
 // AMR kernels (vrt_amr.cu, compiled with -fmad=false)
 int vrt_amr_upload_connectivity(vrt_ctx* c, int s, const vrt_conn& C);

@@ -246,27 +246,83 @@ int vrt_split_substep(vrt_ctx* c, int s, int depth, const double* d_dt, int step
     return 0;
 }
 
+// The same sub-step for every level of the species in one launch (blockIdx.y runs over the whole patch table).  Inside a
+// sub-step the levels do not interact: each kernel writes its own patch's planes and reads its own f, the 1-D fields and — in
+// the coarse-fine flux matching — only f^(s) of finer patches, which no sub-step-0 kernel writes; the reference's
+// coarse-to-fine level loop (Mesh.cpp:66-70) is therefore order-free.  Used by the stage sequence of vrt_step (fewer, fatter
+// launches: small hierarchies are launch-latency bound); Level::FCTTimeStep keeps the per-level entry above.
+int vrt_amr_level_boundary_fluxes_all(vrt_ctx* c, int s, int step);
+int vrt_split_substep_all(vrt_ctx* c, int s, const double* d_dt, int step, int substep) {
+    VrtSpeciesState& S = c->S[s];
+    if (S.table.empty()) return 0;
+    long mx = 0;
+    for (const VrtPatchDev& T : S.table) mx = std::max(mx, T.npad);
+    const dim3 grid((unsigned)((mx + 255) / 256), (unsigned)S.table.size());
+    const VrtPatchDev* tab = S.d_patches;
+    Sp sp = make_sp(S.sp);
+    if (substep == 0) {
+        k_speeds_faces<<<grid, 256, 0, c->stream>>>(tab, sp, c->F);
+        k_fluxes<<<grid, 256, 0, c->stream>>>(tab, step);
+        c->launches += 2;
+        if (int r = vrt_amr_level_boundary_fluxes_all(c, s, step)) return r;
+        k_rk_combine<<<grid, 256, 0, c->stream>>>(tab, step, d_dt);
+        k_apply<<<grid, 256, 0, c->stream>>>(tab, 0);
+        c->launches += 2;
+    } else if (substep == 1) {
+        k_limiter_r<<<grid, 256, 0, c->stream>>>(tab);
+        k_limiter_c<<<grid, 256, 0, c->stream>>>(tab);
+        c->launches += 2;
+    } else if (substep == 2) {
+        k_apply<<<grid, 256, 0, c->stream>>>(tab, 1);
+        c->launches += 1;
+    } else {
+        k_commit<<<grid, 256, 0, c->stream>>>(tab);
+        c->launches += 1;
+    }
+    VRT_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
 // Mesh::InterpolateRhoAndJToFinestMesh (Mesh.cpp:52-56): per level, patch moments are summed into a level array
 // (Level::CollectRhoAndJ, Level.cpp:42-62) which is then added to the species charge and the total current
 int vrt_fields_level_add(vrt_ctx* c, int s);
 int vrt_fields_level_begin(vrt_ctx* c);
 int vrt_fields_level_accumulate(vrt_ctx* c, const double* chargeR, const double* currentR, int x0, int n);
+// Level::CollectRhoAndJ + the per-level additions of Mesh::InterpolateRhoAndJToFinestMesh for all levels in one pass: thread i
+// (finest x index) forms, level by level from the finest, the level sum over the patches covering i in table (= rectangle)
+// order and adds it to the species charge and the total current — the additions and their order are those of the per-level
+// kernels (vrt_fields_level_begin / _accumulate / _add), so the result is bit-identical.
+struct LevelRanges { int n_levels; int first[16]; int count[16]; };
+__global__ void k_collect_moments(const VrtPatchDev* all, LevelRanges R, double* charges, double* J, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double ch = charges[i], cu = J[i];
+    for (int d = 0; d < R.n_levels; d++) {
+        if (!R.count[d]) continue;
+        double lc = 0.0, lj = 0.0;
+        for (int p = R.first[d]; p < R.first[d] + R.count[d]; p++) {
+            const VrtPatchDev& P = all[p];
+            const int k = i - P.x_pos * P.rtb;
+            if (k >= 0 && k < P.n_x * P.rtb) { lc += P.chargeR[k]; lj += P.currentR[k]; }
+        }
+        ch += lc; cu += lj;
+    }
+    charges[i] = ch; J[i] = cu;
+}
+
 int vrt_split_moments(vrt_ctx* c, int s) {
     VrtSpeciesState& S = c->S[s];
+    if (S.table.empty()) return 0;
     Sp sp = make_sp(S.sp);
-    for (size_t d = 0; d < S.level_patches.size(); d++) {
-        if (S.level_patches[d].empty()) continue;
-        int first = S.level_patches[d][0], mx = 0;
-        for (int p : S.level_patches[d]) mx = std::max(mx, S.table[p].n_x * S.table[p].rtb);
-        k_moments<<<dim3(mx, (unsigned)S.level_patches[d].size()), 128, 0, c->stream>>>(S.d_patches + first, sp, c->F);
-        c->launches += 1;
-        VRT_CUDA(c, cudaGetLastError());
-        if (int r = vrt_fields_level_begin(c)) return r;
-        for (int p : S.level_patches[d]) {
-            const VrtPatchDev& P = S.table[p];
-            if (int r = vrt_fields_level_accumulate(c, P.chargeR, P.currentR, P.x_pos * P.rtb, P.n_x * P.rtb)) return r;
-        }
-        if (int r = vrt_fields_level_add(c, s)) return r;
-    }
+    int mx = 0;
+    for (const VrtPatchDev& T : S.table) mx = std::max(mx, T.n_x * T.rtb);
+    k_moments<<<dim3(mx, (unsigned)S.table.size()), 128, 0, c->stream>>>(S.d_patches, sp, c->F);
+    LevelRanges R{};
+    R.n_levels = (int)S.level_patches.size();
+    if (R.n_levels > 16) { c->err = "vrt_moments: more than 16 levels"; return VRT_ERR_ARG; }
+    for (int d = 0; d < R.n_levels; d++) { R.count[d] = (int)S.level_patches[d].size(); R.first[d] = R.count[d] ? S.level_patches[d][0] : 0; }
+    k_collect_moments<<<(c->F.N + 255) / 256, 256, 0, c->stream>>>(S.d_patches, R, S.d_charges, c->F.J, c->F.N);
+    c->launches += 2;
+    VRT_CUDA(c, cudaGetLastError());
     return 0;
 }
