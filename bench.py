@@ -229,14 +229,19 @@ def main():
     # Advance, and the 1-D arrays fileOutput would write (charge x2, PHI, E_x, a^2, Ey, Ez, By, Bz) D2H.
     d2h = 8 + 8 * (2 * nx + nx + nx + (nx + 1) + 4 * (nx + 4))
     h2d = 13 * 8
+    # host buffers of the 1-D outputs: pinned, as the contract asks for the host side of the timed copies
+    pinned = lambda n: torch.empty(n, dtype=torch.float64, pin_memory=True).numpy()
+    hb = {k: pinned(nx + 1 if k == S.A_SQUARED else nx) for k in (S.CHARGES0, S.CHARGES0 + 1, S.PHI, S.EFIELD, S.A_SQUARED)}
+    hf = {w: pinned(nx + 4) for w in (S.EY, S.EZ, S.BY, S.BZ)}
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         dte = run.calculate_dt()
         run.advance(dte)
-        ctx.get_1d(S.CHARGES0); ctx.get_1d(S.CHARGES0 + 1); ctx.get_1d(S.PHI); ctx.get_1d(S.EFIELD); ctx.get_1d(S.A_SQUARED)
-        for w in (S.EY, S.EZ, S.BY, S.BZ):
-            ctx.download_field(w, 0)
+        for k, buf in hb.items():
+            ctx.get_1d(k, buf)
+        for w, buf in hf.items():
+            ctx.download_field(w, 0, buf)
     barrier()
     e2e_s = time.perf_counter() - t0
     if dist is not None:

@@ -112,16 +112,19 @@ class Context:
     def upload_field(self, which, slot, arr):
         self.call("vrt_field_upload", which, slot, _p(np.ascontiguousarray(arr, dtype=np.float64)))
 
-    def download_field(self, which, slot):
-        out = np.zeros(self.M)
+    def download_field(self, which, slot, out=None):
+        if out is None:
+            out = np.zeros(self.M)
         self.call("vrt_field_download", which, slot, _p(out))
         return out
 
     def set_1d(self, which, arr):
         self.call("vrt_set_1d", which, _p(np.ascontiguousarray(arr, dtype=np.float64)))
 
-    def get_1d(self, which):
-        out = np.zeros(self.N + 1 if which == A_SQUARED else self.N)
+    def get_1d(self, which, out=None):
+        """out: optional preallocated (e.g. pinned) float64 buffer of N (A_SQUARED: N + 1) entries"""
+        if out is None:
+            out = np.zeros(self.N + 1 if which == A_SQUARED else self.N)
         self.call("vrt_get_1d", which, _p(out))
         return out
 
