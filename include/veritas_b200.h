@@ -139,6 +139,12 @@ int vrt_set_option(vrt_ctx* ctx, int option, int value);
  * with r^(depth+quadrature_depth) points per direction; writes states 0 and 1.  SURVEY.md §8(f) item 2. */
 int vrt_init_maxwellian_slab(vrt_ctx* ctx, int s, double xl, double xr, double n0, double T, int quadrature_depth);
 
+/* Rectangle::CalculateEnergy (Rectangle.cpp:284-305), the energy-spectrum diagnostic dN/dp: energyR of one patch (n_p * r^depth
+ * values on the finest p grid: dx * sum over the patch's non-nested cells of the p sub-cell interpolants of state 1).  The
+ * reference accumulates it with a data race; this sum is deterministic.  Level::CollectEnergy,
+ * Mesh::InterpolateEnergyToFinestMesh and EMFieldSolver::AssembleEnergy / DumpEnergy stay on the host (tiny arrays). */
+int vrt_patch_energy(vrt_ctx* ctx, int s, int patch, double* energy_host);
+
 /* ---- checkpoint / restart (no counterpart in the reference) ---------------------------- */
 /* Binary image of the context at a step boundary: hierarchy and f of every species, the 1-D field arrays, PHI, Ex0, the
  * neutralisation charge and the time.  vrt_checkpoint_read needs a context with the same vrt_set_grid (and vrt_set_slab /

@@ -16,7 +16,7 @@
 // usage: ref_harness out.bin nx np Lfinest density steps [key=value ...]
 //   keys: dump_every=1 stage_dumps=0 regrid_every=0 threads=N refine_mode=0 tail_p0=2 pre_steps=-1
 //         time_only=0 internals=0 a0=1 file_output=0 (every N steps: SolverManager::fileOutput + OutputRectangles into
-//         ./output, which must exist with its rectangleData subdirectory) precision=15
+//         ./output, which must exist with its rectangleData subdirectory) precision=15 energy=0 (dN/dp dump; use threads=1)
 #include "veritas.hpp"
 #include "Settings.hpp"
 #include "SolverManager.hpp"
@@ -123,7 +123,7 @@ int main(int argc, char** argv) {
     std::map<std::string, double> kv = {{"dump_every", 1}, {"stage_dumps", 0}, {"regrid_every", 0}, {"threads", 0},
                                         {"refine_mode", 0}, {"tail_p0", 2}, {"pre_steps", -1}, {"time_only", 0},
                                         {"internals", 0}, {"a0", 1}, {"np_ion", 0},
-                                        {"file_output", 0}, {"precision", 15}};
+                                        {"file_output", 0}, {"precision", 15}, {"energy", 0}};
     for (int i = 7; i < argc; i++) {
         std::string a = argv[i]; size_t e = a.find('=');
         if (e == std::string::npos || !kv.count(a.substr(0, e))) { fprintf(stderr, "bad arg %s\n", argv[i]); return 2; }
@@ -148,7 +148,8 @@ int main(int argc, char** argv) {
     particles.pmin = {0.1, 0.1};
     const int file_output = (int)kv["file_output"];
     output.precision = (int)kv["precision"];
-    output.energy = false;      // dN/dp: diagnostic with a data race in the reference, not reproduced
+    // dN/dp: the reference accumulates it with a data race — only deterministic with threads=1
+    output.energy = kv["energy"] != 0;
     if (!file_output) output.time = output.rectangleData = output.charge = output.potential = output.EFieldLongitudinal =
         output.EFieldTransverse = output.BFieldTransverse = output.AFieldSquared = false;
 

@@ -337,3 +337,20 @@ def test_fused_equals_split_ragged_sizes(nx, np_e, np_i):
         run.ctx.close()
     errs = [rel_l2(b, a) for a, b in zip(res[S.PATH_SPLIT], res[S.PATH_FUSED])]
     assert max(errs[:2]) < 1e-12 and max(errs[2:]) < 1e-11, errs
+
+
+def test_energy_spectrum_fused_equals_split_and_counts_particles():
+    """Rectangle::CalculateEnergy (dN/dp diagnostic) on slab storage against the per-patch kernel, and its defining property:
+    sum_j energy[j] * dp = particle number (sum of f dx dp)."""
+    res = {}
+    for path in (S.PATH_SPLIT, S.PATH_FUSED):
+        run = vb.LaserPlasmaRun(300, 200, density=0.3, path=path)
+        run.init_device()
+        res[path] = [run.ctx.patch_energy(s, 0) for s in range(2)]
+        if path == S.PATH_FUSED:
+            for s in range(2):
+                f = run.ctx.download_f(s, 0, 1)[2:-2, 2:-2]
+                assert res[path][s].sum() == pytest.approx(f.sum() * run.dx, rel=1e-13)
+        run.ctx.close()
+    for a, b in zip(res[S.PATH_SPLIT], res[S.PATH_FUSED]):
+        assert a.max() > 0 and rel_l2(b, a) < 1e-14

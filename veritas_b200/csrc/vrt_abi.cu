@@ -549,6 +549,14 @@ int vrt_moments_species(vrt_ctx* c, int s, double* charge_host, double* j_host) 
     return moments_impl(c);
 }
 
+// Rectangle::CalculateEnergy (Rectangle.cpp:284-305): the patch's contribution to dN/dp on the finest p grid
+int vrt_patch_energy(vrt_ctx* c, int s, int patch, double* energy_host) {
+    if (int r = ready_species(c, s)) return r;
+    if (!check(c, energy_host && patch >= 0 && patch < (int)c->S[s].desc.size(), "vrt_patch_energy: bad arguments")) return VRT_ERR_ARG;
+    if (!check(c, c->n_ranks == 1, "vrt_patch_energy: single-rank contexts only")) return VRT_ERR_STATE;
+    return vrt_split_patch_energy(c, s, patch, energy_host);
+}
+
 int vrt_enforce_neutralization(vrt_ctx* c) {
     if (int r = ready(c)) return r;
     if (int r = moments_impl(c)) return r;

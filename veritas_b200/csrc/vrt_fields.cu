@@ -93,7 +93,6 @@ __global__ void k_field_faces(VrtFields F) {
 // tridiag(-1, 2, -1).  T^-1 is a convolution with C rho^|k| (rho = 7 - sqrt(48), C = 6/sqrt(48)); rho^18 < 3e-21,
 // so 17 terms per side are exact to fp64.  D y = z with y_0 = 0 is two running sums.  O(N), no N x N matrix.
 constexpr int PK = 17;
-constexpr int PT = 1024;
 
 __device__ double block_sum(double v, double* sh) {
     __syncthreads();
@@ -397,25 +396,6 @@ int vrt_fields_assemble_begin(vrt_ctx* c) {
 }
 int vrt_fields_assemble_add(vrt_ctx* c, int s, const double* chargeR, const double* currentR, int x0, int n) {
     k_add_moments<<<grid1(n), 256, 0, c->stream>>>(c->S[s].d_charges, c->F.J, chargeR, currentR, x0, n);
-    c->launches += 1;
-    VRT_CUDA(c, cudaGetLastError());
-    return 0;
-}
-// Level::CollectRhoAndJ (Level.cpp:42-62): chargeL / currentL live in the first 2N doubles of the Poisson workspace
-int vrt_fields_level_begin(vrt_ctx* c) {
-    k_zero2<<<grid1(c->F.N), 256, 0, c->stream>>>(c->F.scratch, c->F.scratch + c->F.N, c->F.N);
-    c->launches += 1;
-    VRT_CUDA(c, cudaGetLastError());
-    return 0;
-}
-int vrt_fields_level_accumulate(vrt_ctx* c, const double* chargeR, const double* currentR, int x0, int n) {
-    k_add_moments<<<grid1(n), 256, 0, c->stream>>>(c->F.scratch, c->F.scratch + c->F.N, chargeR, currentR, x0, n);
-    c->launches += 1;
-    VRT_CUDA(c, cudaGetLastError());
-    return 0;
-}
-int vrt_fields_level_add(vrt_ctx* c, int s) {
-    k_add_moments<<<grid1(c->F.N), 256, 0, c->stream>>>(c->S[s].d_charges, c->F.J, c->F.scratch, c->F.scratch + c->F.N, 0, c->F.N);
     c->launches += 1;
     VRT_CUDA(c, cudaGetLastError());
     return 0;

@@ -174,6 +174,7 @@ struct vrt_ctx {
 int vrt_split_substep(vrt_ctx* c, int s, int depth, const double* d_dt, int step, int substep);
 int vrt_split_substep_all(vrt_ctx* c, int s, const double* d_dt, int step, int substep);
 int vrt_split_moments(vrt_ctx* c, int s);
+int vrt_split_patch_energy(vrt_ctx* c, int s, int patch, double* host_energy);
 // AMR kernels (vrt_amr.cu, compiled with -fmad=false)
 int vrt_amr_upload_connectivity(vrt_ctx* c, int s, const vrt_conn& C);
 int vrt_amr_level_pass(vrt_ctx* c, int s, int depth, int type, int val);

@@ -196,9 +196,82 @@ __global__ void __launch_bounds__(128) k_moments(const VrtPatchDev* patches, Sp 
     }
 }
 
+// Rectangle::CalculateEnergy (Rectangle.cpp:284-305), race-free: energyR[j * rtb + k] = dx * sum over the non-nested cells of
+// the patch's row j of sub-cell k of GetInterpolantsREL along p (no mean correction there).  One block per
+// (p sub-cell, patch); threads stride over x, fixed-order tree.  The reference accumulates this inside `omp parallel for` over i
+// without a reduction clause (a data race); the sum here is deterministic.
+__global__ void __launch_bounds__(128) k_energy(const VrtPatchDev* patches, int patch, double* out) {
+    const VrtPatchDev& P = patches[patch];
+    const int rtb = P.rtb;
+    const int j = blockIdx.x / rtb, k = blockIdx.x % rtb;
+    const double tl = -0.5 + k / (double)rtb, tr = -0.5 + (k + 1.0) / (double)rtb;
+    const double c0 = (tl + tr) * 0.5;
+    const double c1 = (tl * tl + tl * tr + tr * tr) / 3.0 - (1.0 / 12);
+    const double c2 = (tl * tl * tl + tl * tl * tr + tl * tr * tr + tr * tr * tr) * 0.25;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < P.n_x; i += blockDim.x) {
+        const long c = NS(P, i, j);
+        if (P.flags[c] & VRT_NESTED) continue;
+        double f1 = P.f1[c - 2], f2 = P.f1[c - 1], f3 = P.f1[c], f4 = P.f1[c + 1], f5 = P.f1[c + 2];
+        f5 -= f3; f4 -= f3; f2 -= f3; f1 -= f3;
+        const double a1 = c_IM[0] * f1 + c_IM[1] * f2 + c_IM[2] * f4 + c_IM[3] * f5;
+        const double a2 = c_IM[4] * f1 + c_IM[5] * f2 + c_IM[6] * f4 + c_IM[7] * f5;
+        const double a3 = c_IM[8] * f1 + c_IM[9] * f2 + c_IM[10] * f4 + c_IM[11] * f5;
+        acc += c0 * a1 + c1 * a2 + c2 * a3 + f3;
+    }
+    __shared__ double sh[4];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) out[blockIdx.x] = ((sh[0] + sh[1]) + (sh[2] + sh[3])) * P.dx;
+}
+// the same on slab storage (rtb = 1: the interpolation is the identity): column sums over x in two passes
+__global__ void k_slab_energy_partial(const double* f1p, int n_x, int n_p, int gx, int pitch, int chunk, double* partial) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_p) return;
+    const int x0 = blockIdx.y * chunk, x1 = min(n_x, x0 + chunk);
+    double acc = 0.0;
+    for (int i = x0; i < x1; i++) acc += f1p[(long)(i + gx) * pitch + VRT_SLAB_GH + j];
+    partial[(long)blockIdx.y * n_p + j] = acc;
+}
+__global__ void k_slab_energy_finish(const double* partial, int n_p, int n_chunks, double dx, double* out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_p) return;
+    double acc = 0.0;
+    for (int k = 0; k < n_chunks; k++) acc += partial[(long)k * n_p + j];
+    out[j] = acc * dx;
+}
+
 inline Sp make_sp(const VrtSpecies& s) { return Sp{s.m, s.q, s.pmin, 1 / s.m}; }
 
 }  // namespace
+
+// Rectangle::CalculateEnergy for one patch; host_energy receives n_p * rtb values (Rectangle::energyR)
+int vrt_split_patch_energy(vrt_ctx* c, int s, int patch, double* host_energy) {
+    VrtSpeciesState& S = c->S[s];
+    double* d = nullptr;
+    long n;
+    if (S.path == VRT_PATH_FUSED) {
+        const VrtSlabDev& L = S.slab;
+        n = L.n_p;
+        const int chunks = std::max(1, std::min(256, L.n_x / 64)), chunk = (L.n_x + chunks - 1) / chunks;
+        VRT_CUDA(c, cudaMalloc(&d, sizeof(double) * n * (chunks + 1)));
+        k_slab_energy_partial<<<dim3((unsigned)((n + 127) / 128), chunks), 128, 0, c->stream>>>(L.f[S.i_f1], L.n_x, L.n_p, L.gx, L.pitch, chunk, d + n);
+        k_slab_energy_finish<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(d + n, L.n_p, chunks, L.dx, d);
+    } else {
+        const VrtPatchDev& P = S.patches[patch];
+        n = (long)P.n_p * P.rtb;
+        VRT_CUDA(c, cudaMalloc(&d, sizeof(double) * n));
+        k_energy<<<(unsigned)n, 128, 0, c->stream>>>(S.d_patches, S.table_index[patch], d);
+    }
+    c->launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host_energy, d, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) { c->err = std::string("vrt_patch_energy: ") + cudaGetErrorString(e); return VRT_ERR_CUDA; }
+    return 0;
+}
 
 int vrt_split_init_tables(vrt_ctx* c) {
     if (!g_tabs_loaded) { VRT_CUDA(c, cudaMemcpyToSymbol(c_tabs, &kTableau, sizeof(VrtTableau))); g_tabs_loaded = true; }
@@ -285,13 +358,10 @@ int vrt_split_substep_all(vrt_ctx* c, int s, const double* d_dt, int step, int s
 
 // Mesh::InterpolateRhoAndJToFinestMesh (Mesh.cpp:52-56): per level, patch moments are summed into a level array
 // (Level::CollectRhoAndJ, Level.cpp:42-62) which is then added to the species charge and the total current
-int vrt_fields_level_add(vrt_ctx* c, int s);
-int vrt_fields_level_begin(vrt_ctx* c);
-int vrt_fields_level_accumulate(vrt_ctx* c, const double* chargeR, const double* currentR, int x0, int n);
 // Level::CollectRhoAndJ + the per-level additions of Mesh::InterpolateRhoAndJToFinestMesh for all levels in one pass: thread i
 // (finest x index) forms, level by level from the finest, the level sum over the patches covering i in table (= rectangle)
-// order and adds it to the species charge and the total current — the additions and their order are those of the per-level
-// kernels (vrt_fields_level_begin / _accumulate / _add), so the result is bit-identical.
+// order and adds it to the species charge and the total current — the additions and their order are those of the reference's
+// per-level loops (chargeL = sum over rectangles, then charges += chargeL).
 struct LevelRanges { int n_levels; int first[16]; int count[16]; };
 __global__ void k_collect_moments(const VrtPatchDev* all, LevelRanges R, double* charges, double* J, int N) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -304,6 +304,20 @@ void Level::PushData(int updateType, int val) {
     if (rectangles.empty()) return;
     settings.Check(vrt_level_push(settings.Gpu(), particleType, depth, updateType, val), "vrt_level_push");
 }
+// Level::CollectEnergy (Level.cpp:64-78): Rectangle::CalculateEnergy on the device (vrt_patch_energy), level sum on the host
+void Level::CollectEnergy() {
+    energyL.assign(settings.p_size_finest[particleType], 0.0);
+    for (auto& r : rectangles) {
+        settings.Check(vrt_patch_energy(settings.Gpu(), particleType, r->patch_id, r->energyR.data()), "vrt_patch_energy");
+        const int shift = r->p_pos, rtb = r->relativeToBottom;
+        for (size_t i = 0; i < r->energyR.size(); i++) energyL[shift * rtb + i] += r->energyR[i];
+    }
+}
+void Level::InterpolateEnergyToFinestMesh(std::vector<double>& energy) {     // Level.cpp:31-40
+    CollectEnergy();
+    const unsigned int n = settings.p_size_finest[particleType];
+    for (unsigned int i = 0; i < n; i++) energy[i] += energyL[i];
+}
 // this = new level, `level` = the old one (Level.cpp:128-150): every old rectangle feeds every new one
 void Level::GetDataFromSameLevel(const std::unique_ptr<Level>& level) {
     for (auto& src : level->rectangles) for (auto& dst : rectangles) src->GetDataFromSameLevelRectangle(dst);
@@ -363,6 +377,10 @@ void Mesh::PushBoundaryC() { settings.Check(vrt_push_boundary_c(settings.Gpu(), 
 
 void Mesh::InterpolateRhoAndJToFinestMesh(std::vector<double>& charge, std::vector<double>& J) {
     settings.Check(vrt_moments_species(settings.Gpu(), particleType, charge.data(), J.data()), "vrt_moments_species");
+}
+
+void Mesh::InterpolateEnergyToFinestMesh(std::vector<double>& energy) {     // Mesh.cpp:58-62
+    for (auto& lvl : levels) lvl->InterpolateEnergyToFinestMesh(energy);
 }
 
 void Mesh::SyncHost() {
@@ -683,7 +701,12 @@ EMFieldSolver::~EMFieldSolver() {
 }
 
 void EMFieldSolver::AssembleRhoAndJ() { settings.Check(vrt_moments(settings.Gpu()), "vrt_moments"); mirrors_current_ = false; }
-void EMFieldSolver::AssembleEnergy() {}   // energy spectrum: diagnostic, out of scope
+// EMFieldSolver::AssembleEnergy (EMSolver.cpp:124-131): dN/dp per species on the finest p grid
+void EMFieldSolver::AssembleEnergy() {
+    if (energies.empty()) for (unsigned int i = 0; i < meshes.size(); i++) energies.push_back(std::vector<double>(settings.p_size_finest[i], 0.0));
+    for (auto& e : energies) std::fill(e.begin(), e.end(), 0.0);
+    for (unsigned int i = 0; i < meshes.size(); i++) meshes[i]->InterpolateEnergyToFinestMesh(energies[i]);
+}
 void EMFieldSolver::UpdatePotential() { settings.Check(vrt_poisson(settings.Gpu()), "vrt_poisson"); mirrors_current_ = false; }
 // EMFieldSolver::RGKStep (EMSolver.cpp:194-202); the laser inflow values are the user's GetBY/GetBZ at the current settings.time
 void EMFieldSolver::RGKStep(int step, double timestep) {
@@ -750,7 +773,16 @@ void EMFieldSolver::DumpCharge() {
     if (!chargeStream) chargeStream = open_dump("output/charge.txt", settings.output.precision);
     for (auto& c : charges) write_row(*chargeStream, c.data(), c.size());
 }
-void EMFieldSolver::DumpEnergy() {}
+void EMFieldSolver::DumpEnergy() {                             // EMSolver.cpp:362-379: one file per species, one line per call
+    if (energyStreams.empty())
+        for (unsigned int i = 0; i < settings.q.size(); i++) {
+            std::stringstream name;
+            name << "output/dNdP_" << i << ".txt";
+            energyStreams.push_back(std::make_unique<std::ofstream>(name.str()));
+            (*energyStreams[i]) << std::scientific << std::setprecision(settings.output.precision);
+        }
+    for (unsigned int k = 0; k < settings.q.size() && k < energies.size(); k++) write_row(*energyStreams[k], energies[k].data(), energies[k].size());
+}
 void EMFieldSolver::DumpEFieldLongitudinal() {
     SyncHost();
     if (!ELongStream) ELongStream = open_dump("output/EFieldLong.txt", settings.output.precision);
@@ -864,6 +896,7 @@ void SolverManager::OutputRectangles(double t) {
 }
 void SolverManager::fileOutput(double t) {                 // SolverManager.cpp:102-160 (sequential: the mirrors are shared)
     const Output& o = settings.output;
+    if (o.energy) { EMSolver->AssembleEnergy(); EMSolver->DumpEnergy(); }
     if (o.charge) EMSolver->DumpCharge();
     if (o.potential) EMSolver->DumpPotential();
     if (o.EFieldLongitudinal) EMSolver->DumpEFieldLongitudinal();

@@ -179,6 +179,10 @@ public:
     void GetDataFromSameLevel(const std::unique_ptr<Level>& level);
     void GetDataFromCoarserLevel(const std::unique_ptr<Level>& level);
     void GetDataFromCoarseNewLevel(const std::unique_ptr<Level>& level);
+    void CollectEnergy();                                               // Level.cpp:64-78
+    void InterpolateEnergyToFinestMesh(std::vector<double>& energy);    // Level.cpp:31-40
+private:
+    std::vector<double> energyL;
 };
 
 // ---- Mesh (Mesh.hpp:4-41): one species, hierarchy + regridding on the host ------------------------------------------------------
@@ -197,6 +201,7 @@ public:
     void Advance(double timeStep, int step);
     void PushBoundaryC();
     void InterpolateRhoAndJToFinestMesh(std::vector<double>& charge, std::vector<double>& J);
+    void InterpolateEnergyToFinestMesh(std::vector<double>& energy);
     void SetFieldSolver(const std::shared_ptr<EMFieldSolver>& solver);
     void updateHierarchy(bool init = false);
     void outputRectangleData(double tidx);
@@ -226,7 +231,8 @@ class EMFieldSolver {
     std::vector<std::shared_ptr<Mesh>> meshes;
     std::ofstream *chargeStream, *ELongStream, *ETransStream, *potentialStream, *BStream, *AsqStream, *timeStream;
     std::vector<double> charge, J, By, Bz, Ey, Ez, Ay, Az, a_squared, neutralizationCharge;   // host mirrors
-    std::vector<std::vector<double>> charges;
+    std::vector<std::vector<double>> charges, energies;
+    std::vector<std::unique_ptr<std::ofstream>> energyStreams;
     double* PHI;
     double fieldCoef, Ex0;
     bool mirrors_current_ = false;

@@ -74,6 +74,13 @@ class Context:
     def set_path(self, path):
         self.call("vrt_set_path", path)
 
+    def patch_energy(self, s, patch):
+        """Rectangle::CalculateEnergy of one patch: n_p * r^depth values"""
+        p = self.patches[s][patch]
+        out = np.zeros(p["n_p"] * 2 ** p.get("depth", 0))
+        self.call("vrt_patch_energy", s, patch, _p(out))
+        return out
+
     def checkpoint_write(self, path):
         self.call("vrt_checkpoint_write", str(path).encode())
 
