@@ -11,6 +11,7 @@ int vrt_fields_refresh_efield(vrt_ctx* c);
 int vrt_init_kernels_maxwellian(vrt_ctx* c, int s, double xl, double xr, double n0, double T, int quadrature_depth);
 int vrt_comm_halo_exchange(vrt_ctx* c, int s);
 int vrt_comm_gather_moments(vrt_ctx* c);
+int vrt_comm_wait_halo(vrt_ctx* c, int s);
 void vrt_comm_destroy(vrt_ctx* c);
 int vrt_fields_init_tables(vrt_ctx* c);
 int vrt_split_init_tables(vrt_ctx* c);
@@ -575,6 +576,9 @@ static int vlasov_stage_impl(vrt_ctx* c, int s, const double* d_dt, int step) {
     VrtSpeciesState& S = c->S[s];
     int r;
     if (S.path == VRT_PATH_FUSED) {
+        // x-slabs: the kernel reads the halo columns the previous exchange of this species delivered; its own exchange runs
+        // on the communication stream and overlaps whatever the compute stream does next
+        if (c->n_ranks > 1 && (r = vrt_comm_wait_halo(c, s))) return r;
         if ((r = vrt_fused_stage(c, s, d_dt, step))) return r;
         if (c->n_ranks > 1 && (r = vrt_comm_halo_exchange(c, s))) return r;
         return 0;
@@ -595,7 +599,8 @@ int vrt_vlasov_stage(vrt_ctx* c, int s, double dt, int step) {
     if (!check(c, s >= 0 && s < c->n_species && step >= 0 && step <= 5, "vrt_vlasov_stage: bad arguments")) return VRT_ERR_ARG;
     if (int r = set_params_async(c, dt, nullptr)) return r;
     if (step == 0) if (int r = vrt_fields_snapshot_stage0(c)) return r;
-    return vlasov_stage_impl(c, s, &c->d_params->dt, step);
+    if (int r = vlasov_stage_impl(c, s, &c->d_params->dt, step)) return r;
+    return c->n_ranks > 1 ? vrt_comm_wait_halo(c, s) : 0;
 }
 
 int vrt_vlasov_substep(vrt_ctx* c, int s, int depth, double dt, int step, int substep) {
@@ -696,6 +701,7 @@ static int enqueue_step(vrt_ctx* c) {
         if ((r = vlasov_stages_all(c, i))) return r;
         if ((r = vrt_fields_rhs_update_faces(c, i, c->d_params))) return r;
     }
+    if (c->n_ranks > 1 && (r = vrt_comm_wait_halo(c, -1))) return r;      // a finished step has its halos in place
     return 0;
 }
 

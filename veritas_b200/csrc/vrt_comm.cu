@@ -57,9 +57,19 @@ extern "C" int vrt_comm_init(vrt_ctx* c, const void* unique_id128, int rank, int
     ncclComm_t comm;
     VRT_NCCL(c, g_nccl.CommInitRank(&comm, n_ranks, id, rank));
     c->nccl_comm = comm;
+    if (!c->comm_stream) {
+        VRT_CUDA(c, cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+        VRT_CUDA(c, cudaEventCreateWithFlags(&c->ev_m, cudaEventDisableTiming));
+        VRT_CUDA(c, cudaEventCreateWithFlags(&c->ev_ag, cudaEventDisableTiming));
+        for (auto& S : c->S) {
+            VRT_CUDA(c, cudaEventCreateWithFlags(&S.ev_k, cudaEventDisableTiming));
+            VRT_CUDA(c, cudaEventCreateWithFlags(&S.ev_h, cudaEventDisableTiming));
+        }
+    }
     return 0;
 }
 
+// halo exchange of species s behind its stage kernel: enqueued on the communication stream, signalled through S.ev_h
 int vrt_comm_halo_exchange(vrt_ctx* c, int s) {
     if (!c->nccl_comm) { c->err = "multi-rank context without vrt_comm_init"; return VRT_ERR_STATE; }
     VrtSpeciesState& S = c->S[s];
@@ -67,6 +77,11 @@ int vrt_comm_halo_exchange(vrt_ctx* c, int s) {
     ncclComm_t comm = (ncclComm_t)c->nccl_comm;
     double* f = L.f[S.i_f1];
     const size_t n = (size_t)L.gx * L.pitch;
+    cudaStream_t main_stream = c->stream;
+    VRT_CUDA(c, cudaEventRecord(S.ev_k, main_stream));
+    VRT_CUDA(c, cudaStreamWaitEvent(c->comm_stream, S.ev_k, 0));
+    struct Restore { vrt_ctx* c; cudaStream_t s; ~Restore() { c->stream = s; } } restore{c, main_stream};
+    c->stream = c->comm_stream;
     VRT_NCCL(c, g_nccl.GroupStart());
     if (c->rank > 0) {
         VRT_NCCL(c, g_nccl.Send(f + (long)L.gx * L.pitch, n, ncclDouble, c->rank - 1, comm, c->stream));        // own columns [0,3)
@@ -77,21 +92,47 @@ int vrt_comm_halo_exchange(vrt_ctx* c, int s) {
         VRT_NCCL(c, g_nccl.Recv(f + (long)(L.n_x + L.gx) * L.pitch, n, ncclDouble, c->rank + 1, comm, c->stream));   // halo [n_x,n_x+3)
     }
     VRT_NCCL(c, g_nccl.GroupEnd());
+    VRT_CUDA(c, cudaEventRecord(S.ev_h, c->comm_stream));
+    S.halo_pending = true;
     return 0;
 }
 
+// the stream the context computes on waits for the outstanding halo exchange of species s (all species: s < 0)
+int vrt_comm_wait_halo(vrt_ctx* c, int s) {
+    for (int k = 0; k < c->n_species; k++) {
+        VrtSpeciesState& S = c->S[k];
+        if ((s < 0 || s == k) && S.halo_pending) { VRT_CUDA(c, cudaStreamWaitEvent(c->stream, S.ev_h, 0)); S.halo_pending = false; }
+    }
+    return 0;
+}
+
+// all-gather of the slab moments, on the communication stream between two events of the compute stream
 int vrt_comm_gather_moments(vrt_ctx* c) {
     if (!c->nccl_comm) { c->err = "multi-rank context without vrt_comm_init"; return VRT_ERR_STATE; }
     ncclComm_t comm = (ncclComm_t)c->nccl_comm;
     const size_t n = (size_t)(c->x_end - c->x_begin);
+    cudaStream_t main_stream = c->stream;
+    VRT_CUDA(c, cudaEventRecord(c->ev_m, main_stream));
+    VRT_CUDA(c, cudaStreamWaitEvent(c->comm_stream, c->ev_m, 0));
+    struct Restore { vrt_ctx* c; cudaStream_t s; ~Restore() { c->stream = s; } } restore{c, main_stream};
+    c->stream = c->comm_stream;
     VRT_NCCL(c, g_nccl.GroupStart());
     for (int s = 0; s < c->n_species; s++)
         VRT_NCCL(c, g_nccl.AllGather(c->S[s].d_charges + c->x_begin, c->S[s].d_charges, n, ncclDouble, comm, c->stream));
     VRT_NCCL(c, g_nccl.AllGather(c->F.J + c->x_begin, c->F.J, n, ncclDouble, comm, c->stream));
     VRT_NCCL(c, g_nccl.GroupEnd());
+    VRT_CUDA(c, cudaEventRecord(c->ev_ag, c->comm_stream));
+    VRT_CUDA(c, cudaStreamWaitEvent(main_stream, c->ev_ag, 0));
     return 0;
 }
 
 void vrt_comm_destroy(vrt_ctx* c) {
+    if (c->comm_stream) {
+        cudaStreamSynchronize(c->comm_stream);
+        for (auto& S : c->S) { if (S.ev_k) cudaEventDestroy(S.ev_k); if (S.ev_h) cudaEventDestroy(S.ev_h); S.ev_k = S.ev_h = nullptr; }
+        if (c->ev_m) cudaEventDestroy(c->ev_m);
+        if (c->ev_ag) cudaEventDestroy(c->ev_ag);
+        cudaStreamDestroy(c->comm_stream); c->comm_stream = nullptr;
+    }
     if (c->nccl_comm && g_nccl.CommDestroy) { g_nccl.CommDestroy((ncclComm_t)c->nccl_comm); c->nccl_comm = nullptr; }
 }

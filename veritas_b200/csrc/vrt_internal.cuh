@@ -126,6 +126,10 @@ struct VrtSpeciesState {
     VrtSlabDev slab;
     int i_f0 = 0, i_f1 = 0;              // indices into slab.f: f^n and current stage value
     double* d_charges = nullptr;         // per-species charge on the finest grid (N)
+    // x-slab runs: the halo exchange of this species runs on the context's communication stream behind ev_k (stage kernel done)
+    // and signals ev_h; the next stage kernel of the species waits for it (halo_pending)
+    cudaEvent_t ev_k = nullptr, ev_h = nullptr;
+    bool halo_pending = false;
 };
 
 struct vrt_ctx {
@@ -143,6 +147,10 @@ struct vrt_ctx {
     // slab decomposition
     int rank = 0, n_ranks = 1, x_begin = 0, x_end = 0;
     void* nccl_comm = nullptr;
+    // every NCCL call of the context is issued on comm_stream, in the same order on all ranks (halo s = 0, 1, ..., moment
+    // all-gather, ...), so that the exchanges overlap the other species' stage kernel, the 1-D field update and the moments
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_m = nullptr, ev_ag = nullptr;
     // step graph
     VrtStepParams* d_params = nullptr; VrtStepParams* h_params = nullptr;
     cudaGraphExec_t graph_step3[3] = {nullptr, nullptr, nullptr};   // keyed by the plane-rotation state at step start
