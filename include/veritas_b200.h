@@ -132,7 +132,7 @@ int vrt_step_fields(vrt_ctx* ctx, double dt, const double laser[12]);
 long vrt_last_step_launches(const vrt_ctx* ctx);
 
 /* option 0: replay vrt_step through a captured CUDA graph (default 1) or launch kernel by kernel (0);
- * option 1: run the species' Vlasov stages of one RK stage on concurrent streams / graph branches (default 1; single-rank contexts) */
+ * option 1: run the species' Vlasov stages of one RK stage on concurrent streams / graph branches (default 1) */
 int vrt_set_option(vrt_ctx* ctx, int option, int value);
 /* Rectangle::InitializeDistribution (Rectangle.cpp:616-665) for the shipped Maxwellian slab
  * (Settings::InitialDistribution, veritas.cpp:107-115), evaluated on the device: sub-cell midpoint quadrature

@@ -662,7 +662,8 @@ double vrt_update_time(double time, int step, double dt) {   // Settings::Update
 // halves the launch-latency-bound time of small and AMR hierarchies and fills the tail of the last wave of large kernels.
 static int vlasov_stages_all(vrt_ctx* c, int i) {
     int r;
-    const bool fork = c->fork_species && c->n_ranks == 1 && c->n_species > 1;
+    // (x-slab runs too: the NCCL calls all go to the communication stream, in host order, whichever stream computes)
+    const bool fork = c->fork_species && c->n_species > 1;
     if (!fork) {
         for (int s = 0; s < c->n_species; s++) if ((r = vlasov_stage_impl(c, s, &c->d_params->dt, i))) return r;
         return 0;

@@ -161,7 +161,7 @@ struct vrt_ctx {
     long launches = 0, last_step_launches = 0;
     double* d_comm = nullptr; long comm_doubles = 0;   // staging buffer for the moment all-gather
     // the species' Vlasov stages of one RK stage are independent: species s > 0 runs on aux_stream[s - 1] between a fork and a
-    // join event (parallel branches of the step graph; single-rank contexts only — NCCL calls of one communicator stay ordered)
+    // join event (parallel branches of the step graph; on x-slab runs the NCCL calls still go to comm_stream in host order)
     std::vector<cudaStream_t> aux_stream;
     std::vector<cudaEvent_t> aux_join;
     cudaEvent_t ev_fork = nullptr;
