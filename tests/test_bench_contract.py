@@ -1,0 +1,34 @@
+"""bench.py contract checks that need no GPU: the reference arm runs the compiled reference (oracle/_ref) on the host cores
+and prints one JSON line with the agreed keys; our arm refuses to run without a CUDA device (no CPU fallback)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/ref_harness not built (run __graft_entry__.build())")
+def test_reference_arm_json_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["metric"] == "phase-space cell-updates/s per RK stage" and d["unit"] == "cell-updates/s"
+    assert d["higher_is_better"] is True and d["value"] > 1e5 and d["dtype"] == "f64"
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == d["value"] and "config 1" in cb["sample"]
+    assert d["gpu_launches"] == 0 and d["steps"] == 1 and d["warmup"] == 1
+
+
+def test_our_arm_needs_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                       text=True, timeout=600)
+    assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
