@@ -17,6 +17,13 @@
 //   keys: dump_every=1 stage_dumps=0 regrid_every=0 threads=N refine_mode=0 tail_p0=2 pre_steps=-1
 //         time_only=0 internals=0 a0=1 file_output=0 (every N steps: SolverManager::fileOutput + OutputRectangles into
 //         ./output, which must exist with its rectangleData subdirectory) precision=15 energy=0 (dN/dp dump; use threads=1)
+//
+//        ref_harness cluster cases.txt out.txt nx np Lfinest
+//   runs the regrid clustering members of Mesh (Mesh.cpp:298-792) on the flag sets of cases.txt, one case per line:
+//     split <minEfficiency> <n> x p x p ...        getExtrema + splitRectangle      -> "k x0 p0 x1 p1 ..." (boxes, inclusive corners)
+//     interp <lvl> <k> x0 p0 x1 p1 ...             interpRectanglesUp               -> "k x0 p0 x1 p1 ..."
+//     merge <lvl> x0 p0 x1 p1                      mergeDownFlaggedData             -> "n x p x p ..."
+//   The host build runs them without a Mesh and without a device (tests/test_host_clustering.py).
 #include "veritas.hpp"
 #include "Settings.hpp"
 #include "SolverManager.hpp"
@@ -27,7 +34,9 @@
 #include "../veritas_b200/host/laser_plasma_case.hpp"
 #include <cstdio>
 #include <cstdlib>
+#include <fstream>
 #include <map>
+#include <sstream>
 #include <string>
 
 bool LOUD = false, NOISY = false;
@@ -114,7 +123,96 @@ static void dump_state(SolverManager& SM, Settings& st, const std::string& tag, 
     }
 }
 
+// the laser-plasma case's Input / Particles (veritas.cpp:118-133 with the sizes as parameters)
+static void configure_case(unsigned nx, unsigned np, unsigned np_ion, unsigned Lfinest, Input& grid, Particles& particles) {
+    grid.minEfficiency = 0.75; grid.dx = 0.5; grid.k = 0.01;
+    grid.refinementCriteria = 1e-8; grid.cfl = 0.5; grid.sizeWeight = 0.0;
+    grid.preLength = 0; grid.postLength = 0;
+    grid.nx = nx; grid.r = 2; grid.Lfinest = Lfinest;
+    grid.tempEM = {0.0};
+    particles.mass = {9.10938291e-31, 9.10938291e-31 * 1836};
+    particles.charge = {-1.60217657e-19, 1.60217657e-19};
+    particles.misc = {{0.0, 0.01}, {0.0, 0.01}};
+    particles.np = {np, np_ion};
+    particles.dp = {0.1, 0.1};
+    particles.pmin = {0.1, 0.1};
+}
+
+static void put_boxes(std::ostream& o, const level& L) {
+    o << L.size();
+    for (const rect& r : L) o << ' ' << r.first.first << ' ' << r.first.second << ' ' << r.second.first << ' ' << r.second.second;
+    o << '\n';
+}
+
+// clustering members on given flag sets (see the usage comment)
+static int cluster_mode(int argc, char** argv) {
+    if (argc < 7) { fprintf(stderr, "usage: %s cluster cases.txt out.txt nx np Lfinest\n", argv[0]); return 2; }
+    std::ifstream in(argv[2]);
+    std::ofstream out(argv[3]);
+    if (!in || !out) { fprintf(stderr, "cluster: cannot open %s / %s\n", argv[2], argv[3]); return 1; }
+    g_case.density = 0.1;
+    Input grid; Particles particles; Output output;
+    configure_case(atoi(argv[4]), atoi(argv[5]), atoi(argv[5]), atoi(argv[6]), grid, particles);
+    output.time = output.rectangleData = output.charge = output.potential = output.EFieldLongitudinal =
+        output.EFieldTransverse = output.BFieldTransverse = output.AFieldSquared = output.energy = false;
+    Settings settings(grid, particles, output);
+#ifndef VRT_HOST_BUILD
+    SolverManager SM(settings);
+    Mesh& M = *SM.meshes[0];
+#else
+    // level sizes as Mesh::interpRectanglesUp / mergeDownFlaggedData take them from Settings (species 0)
+    auto nx_of = [&](int lvl) { return settings.GetXSize(settings.maxDepth - lvl); };
+    auto np_of = [&](int lvl) { return settings.GetPSize(settings.maxDepth - lvl, 0); };
+#endif
+    std::string line;
+    while (std::getline(in, line)) {
+        std::istringstream ls(line);
+        std::string kind;
+        if (!(ls >> kind)) continue;
+        if (kind == "split") {
+            double eff; int n;
+            ls >> eff >> n;
+            std::vector<coords> flagged(n);
+            for (coords& c : flagged) ls >> c.first >> c.second;
+            rect ext;
+#ifndef VRT_HOST_BUILD
+            M.getExtrema(ext, flagged);
+            put_boxes(out, M.splitRectangle(ext, flagged, eff));
+#else
+            Mesh::getExtrema(ext, flagged);
+            put_boxes(out, Mesh::splitRectangle(ext, flagged, eff));
+#endif
+        } else if (kind == "interp") {
+            int lvl, k;
+            ls >> lvl >> k;
+            level L(k);
+            for (rect& r : L) ls >> r.first.first >> r.first.second >> r.second.first >> r.second.second;
+#ifndef VRT_HOST_BUILD
+            M.interpRectanglesUp(L, lvl);
+#else
+            Mesh::scaleRectanglesUp(L, nx_of(lvl), np_of(lvl), nx_of(lvl + 1), np_of(lvl + 1));
+#endif
+            put_boxes(out, L);
+        } else if (kind == "merge") {
+            int lvl;
+            rect r;
+            ls >> lvl >> r.first.first >> r.first.second >> r.second.first >> r.second.second;
+            std::vector<coords> found;
+#ifndef VRT_HOST_BUILD
+            M.mergeDownFlaggedData(lvl, r, found);
+#else
+            Mesh::footprintBelow(r, nx_of(lvl), np_of(lvl), nx_of(lvl + 2), np_of(lvl + 2), (int)settings.refinementRatio, found);
+#endif
+            out << found.size();
+            for (const coords& c : found) out << ' ' << c.first << ' ' << c.second;
+            out << '\n';
+        } else { fprintf(stderr, "cluster: unknown case kind %s\n", kind.c_str()); return 2; }
+    }
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 2 && std::string(argv[1]) == "cluster") return cluster_mode(argc, argv);
     if (argc < 7) { fprintf(stderr, "usage: %s out.bin nx np Lfinest density steps [key=value...]\n", argv[0]); return 2; }
     const char* out = argv[1];
     unsigned nx = atoi(argv[2]), np = atoi(argv[3]), Lfinest = atoi(argv[4]);
@@ -134,18 +232,8 @@ int main(int argc, char** argv) {
     bool time_only = kv["time_only"] != 0, internals = kv["internals"] != 0;
 
     Input grid; Particles particles; Output output;
-    grid.minEfficiency = 0.75; grid.dx = 0.5; grid.k = 0.01;
-    grid.refinementCriteria = 1e-8; grid.cfl = 0.5; grid.sizeWeight = 0.0;
-    grid.preLength = 0; grid.postLength = 0;
-    grid.nx = nx; grid.r = 2; grid.Lfinest = Lfinest;
-    grid.tempEM = {0.0};
-    particles.mass = {9.10938291e-31, 9.10938291e-31 * 1836};
-    particles.charge = {-1.60217657e-19, 1.60217657e-19};
-    particles.misc = {{0.0, 0.01}, {0.0, 0.01}};
     unsigned np_ion = kv["np_ion"] > 0 ? (unsigned)kv["np_ion"] : np;
-    particles.np = {np, np_ion};
-    particles.dp = {0.1, 0.1};
-    particles.pmin = {0.1, 0.1};
+    configure_case(nx, np, np_ion, Lfinest, grid, particles);
     const int file_output = (int)kv["file_output"];
     output.precision = (int)kv["precision"];
     // dN/dp: the reference accumulates it with a data race — only deterministic with threads=1

@@ -531,22 +531,22 @@ level Mesh::splitRectangle(rect& box, std::vector<coords>& flagged, const double
 }
 
 // boxes found on hierarchy level lvl become patches of level lvl+1: inclusive upper corner -> exclusive, then scale (Mesh.cpp:298-313)
-void Mesh::interpRectanglesUp(level& identified, const int& lvl) {
-    const int nmax = settings.GetXSize(settings.maxDepth - lvl), pmax = settings.GetPSize(settings.maxDepth - lvl, particleType);
-    const int nmax1 = settings.GetXSize(settings.maxDepth - (lvl + 1)), pmax1 = settings.GetPSize(settings.maxDepth - (lvl + 1), particleType);
+void Mesh::scaleRectanglesUp(level& identified, int nmax, int pmax, int nmax1, int pmax1) {
     for (rect& r : identified) {
         r.second.first += 1; r.second.second += 1;
         r.first.first *= (nmax1 / double(nmax)); r.first.second *= (pmax1 / double(pmax));
         r.second.first *= (nmax1 / double(nmax)); r.second.second *= (pmax1 / double(pmax));
     }
 }
+void Mesh::interpRectanglesUp(level& identified, const int& lvl) {
+    scaleRectanglesUp(identified, settings.GetXSize(settings.maxDepth - lvl), settings.GetPSize(settings.maxDepth - lvl, particleType),
+                      settings.GetXSize(settings.maxDepth - (lvl + 1)), settings.GetPSize(settings.maxDepth - (lvl + 1), particleType));
+}
 
 // cells of level lvl under a patch of level lvl+2 widened by 2r cells (one more on the upper x side), so that the regridded
 // level lvl+1 keeps containing it (Mesh.cpp:315-339); the index scaling truncates towards zero as the reference's int conversion does
-void Mesh::mergeDownFlaggedData(const int& lvl, const rect& r, std::vector<coords>& foundCells) {
-    const int nmax = settings.GetXSize(settings.maxDepth - lvl), pmax = settings.GetPSize(settings.maxDepth - lvl, particleType);
-    const int nmax2 = settings.GetXSize(settings.maxDepth - (lvl + 2)), pmax2 = settings.GetPSize(settings.maxDepth - (lvl + 2), particleType);
-    const int w = 2 * (int)settings.refinementRatio;
+void Mesh::footprintBelow(const rect& r, int nmax, int pmax, int nmax2, int pmax2, int ratio, std::vector<coords>& foundCells) {
+    const int w = 2 * ratio;
     for (int i = r.first.first - w; i <= r.second.first + w + 1; i++)
         for (int j = r.first.second - w; j <= r.second.second + w; j++) {
             const int ic = i * (nmax / double(nmax2)), jc = j * (pmax / double(pmax2));
@@ -554,6 +554,11 @@ void Mesh::mergeDownFlaggedData(const int& lvl, const rect& r, std::vector<coord
         }
     std::sort(foundCells.begin(), foundCells.end());
     foundCells.erase(std::unique(foundCells.begin(), foundCells.end()), foundCells.end());
+}
+void Mesh::mergeDownFlaggedData(const int& lvl, const rect& r, std::vector<coords>& foundCells) {
+    footprintBelow(r, settings.GetXSize(settings.maxDepth - lvl), settings.GetPSize(settings.maxDepth - lvl, particleType),
+                   settings.GetXSize(settings.maxDepth - (lvl + 2)), settings.GetPSize(settings.maxDepth - (lvl + 2), particleType),
+                   (int)settings.refinementRatio, foundCells);
 }
 
 // Mesh::updateHierarchy (Mesh.cpp:132-210): from the finest hierarchy level down, flag -> cluster -> replace the next finer

@@ -205,16 +205,22 @@ public:
     void SetFieldSolver(const std::shared_ptr<EMFieldSolver>& solver);
     void updateHierarchy(bool init = false);
     void outputRectangleData(double tidx);
-    // clustering (Mesh.cpp:341-792)
-    int countCells(const rect& span);
-    std::tuple<std::vector<int>, std::vector<int>, std::vector<int>, std::vector<int>> computeSignatures(rect& rectangle, std::vector<coords>& flagged);
-    coords identifyInflection(rect& rectangle, std::tuple<std::vector<int>, std::vector<int>, std::vector<int>, std::vector<int>>& signatures);
-    std::tuple<bool, int, int> hasHole(std::vector<int>& sig);
-    level splitRectangle(rect& rectangle, std::vector<coords>& flagged, const double& minEfficiency);
+    // clustering (Mesh.cpp:341-792).  Pure functions of their arguments (the reference's touch no member either): static here, so
+    // that they run without a Mesh — and therefore without a device — in the CPU tests (tests/test_host_clustering.py); call
+    // sites written as mesh.splitRectangle(...) keep compiling.
+    static int countCells(const rect& span);
+    static std::tuple<std::vector<int>, std::vector<int>, std::vector<int>, std::vector<int>> computeSignatures(rect& rectangle, std::vector<coords>& flagged);
+    static coords identifyInflection(rect& rectangle, std::tuple<std::vector<int>, std::vector<int>, std::vector<int>, std::vector<int>>& signatures);
+    static std::tuple<bool, int, int> hasHole(std::vector<int>& sig);
+    static level splitRectangle(rect& rectangle, std::vector<coords>& flagged, const double& minEfficiency);
+    static void getExtrema(rect& extrema, const std::vector<coords>& flaggedCells);
     void getError(const int& lvl, bool init, std::vector<coords>& flaggedCells);
     void interpRectanglesUp(level& identified, const int& lvl);
     void mergeDownFlaggedData(const int& lvl, const rect& r, std::vector<coords>& foundCells);
-    void getExtrema(rect& extrema, const std::vector<coords>& flaggedCells);
+    // the index arithmetic of the two members above with the level sizes passed in (n*, p* = cells of the level the boxes are on /
+    // of the target level)
+    static void scaleRectanglesUp(level& identified, int nmax, int pmax, int nmax1, int pmax1);
+    static void footprintBelow(const rect& r, int nmax, int pmax, int nmax2, int pmax2, int ratio, std::vector<coords>& foundCells);
     void promoteHierarchyToMesh(bool init);
     void InterMeshDataTransfer(const std::vector<std::unique_ptr<Level>>& levels_n);
     // veritas_b200 additions
