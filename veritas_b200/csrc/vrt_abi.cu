@@ -131,12 +131,10 @@ int vrt_set_grid(vrt_ctx* c, int N, double dx, int pre, int post, int r, int max
     int rc;
     for (int v = 0; v < 6; v++) if ((rc = dev_alloc(c, c->field_allocs, &F.Y[v], 8L * F.M))) return rc;
     if ((rc = dev_alloc(c, c->field_allocs, &F.a_squared, N + 1))) return rc;
-    if ((rc = dev_alloc(c, c->field_allocs, &F.a_squared0, N + 1))) return rc;
     if ((rc = dev_alloc(c, c->field_allocs, &F.PHI, N))) return rc;
     F.epad = std::max(2, (int)std::lround(std::pow((double)r, max_depth)));
     if (!check(c, F.epad < N / 2, "vrt_set_grid: too many levels for this x size")) return VRT_ERR_ARG;
     if ((rc = dev_alloc(c, c->field_allocs, &F.E, N + 2 * F.epad))) return rc;
-    if ((rc = dev_alloc(c, c->field_allocs, &F.E0, N + 2 * F.epad))) return rc;
     if ((rc = dev_alloc(c, c->field_allocs, &F.charge, N))) return rc;
     if ((rc = dev_alloc(c, c->field_allocs, &F.J, N))) return rc;
     if ((rc = dev_alloc(c, c->field_allocs, &F.neutral, N))) return rc;
@@ -265,9 +263,10 @@ int vrt_set_hierarchy(vrt_ctx* c, int s, int n_patches, const vrt_patch_desc* d)
         // two pooled allocations (uniform plane stride): each is one 3-D tensor {p, column, plane} for the TMA descriptors
         double *fpool, *hpool;
         if ((rc = dev_alloc(c, S.allocations, &fpool, 3 * (size_t)L.plane))) return rc;
-        if ((rc = dev_alloc(c, S.allocations, &hpool, 10 * (size_t)L.plane))) return rc;
+        if ((rc = dev_alloc(c, S.allocations, &hpool, 12 * (size_t)L.plane))) return rc;
         for (int k = 0; k < 3; k++) L.f[k] = fpool + k * L.plane;
         for (int k = 0; k < 5; k++) { L.FxH[k] = hpool + (2 * k) * L.plane; L.FpH[k] = hpool + (2 * k + 1) * L.plane; }
+        L.FxL0 = hpool + 10 * L.plane; L.FpL0 = hpool + 11 * L.plane;
         if ((rc = dev_alloc(c, S.allocations, &L.chargeR, L.n_x))) return rc;
         if ((rc = dev_alloc(c, S.allocations, &L.currentR, L.n_x))) return rc;
         S.i_f0 = S.i_f1 = 0;
@@ -598,7 +597,6 @@ int vrt_vlasov_stage(vrt_ctx* c, int s, double dt, int step) {
     if (int r = ready_species(c, s)) return r;
     if (!check(c, s >= 0 && s < c->n_species && step >= 0 && step <= 5, "vrt_vlasov_stage: bad arguments")) return VRT_ERR_ARG;
     if (int r = set_params_async(c, dt, nullptr)) return r;
-    if (step == 0) if (int r = vrt_fields_snapshot_stage0(c)) return r;
     if (int r = vlasov_stage_impl(c, s, &c->d_params->dt, step)) return r;
     return c->n_ranks > 1 ? vrt_comm_wait_halo(c, s) : 0;
 }
@@ -698,7 +696,6 @@ static int enqueue_step(vrt_ctx* c) {
     for (int i = 0; i < 6; i++) {
         if ((r = moments_impl(c))) return r;
         if ((r = vrt_fields_poisson(c))) return r;
-        if (i == 0 && (r = vrt_fields_snapshot_stage0(c))) return r;
         if ((r = vlasov_stages_all(c, i))) return r;
         if ((r = vrt_fields_rhs_update_faces(c, i, c->d_params))) return r;
     }

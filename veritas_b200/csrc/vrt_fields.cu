@@ -316,10 +316,6 @@ __global__ void k_neutralize(VrtFields F) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < F.N) { F.J[i] = 0.0; F.neutral[i] = -F.charge[i]; }
 }
-__global__ void k_copy(double* dst, const double* src, int n) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = src[i];
-}
 
 bool g_tab_loaded = false;
 inline int grid1(int n, int b = 256) { return (n + b - 1) / b; }
@@ -405,14 +401,6 @@ int vrt_fields_assemble_end(vrt_ctx* c) {
         k_add1<<<grid1(c->F.N), 256, 0, c->stream>>>(c->F.charge, c->S[s].d_charges, c->F.N);
         c->launches += 1;
     }
-    VRT_CUDA(c, cudaGetLastError());
-    return 0;
-}
-int vrt_fields_snapshot_stage0(vrt_ctx* c) {
-    VrtFields& F = c->F;
-    k_copy<<<grid1(F.N + 1), 256, 0, c->stream>>>(F.a_squared0, F.a_squared, F.N + 1);
-    k_copy<<<grid1(F.N + 2 * F.epad), 256, 0, c->stream>>>(F.E0, F.E, F.N + 2 * F.epad);
-    c->launches += 2;
     VRT_CUDA(c, cudaGetLastError());
     return 0;
 }

@@ -34,11 +34,9 @@ struct VrtFields {
     double dx;                  // finest dx
     double* Y[6];               // By,Bz,Ey,Ez,Ay,Az: 8 slots x M, slot-major (Index(i,s) = s*M+i)
     double* a_squared;          // N+1 (x-faces; entry N never written, quirk Q2)
-    double* a_squared0;         // stage-0 snapshot (fused path: low-order flux recompute, quirk Q1)
     double* PHI;                // N
     int epad;                   // E is tabulated on [-epad, N+epad): epad = max(2, r^max_depth) (coarse ghost columns average rtb cells)
     double* E;                  // N+2*epad: E[i+epad] = EMFieldSolver::GetEfield(i)
-    double* E0;                 // stage-0 snapshot of E
     double* charge; double* J; double* neutral;   // N each
     double* Ex0;                // device scalar
     double* scratch;            // Poisson workspace, 4*N
@@ -87,8 +85,8 @@ struct vrt_conn {
 };
 int vrt_conn_derive(vrt_conn& C, int n, const vrt_patch_desc* d, int r, int max_depth);
 
-// Fused-path storage of one full-domain (or x-slab) single-level patch: three rotating f planes and five
-// stored high-order flux pairs.  Rows are x columns (slow), p is contiguous.  GX ghost columns per side.
+// Fused-path storage of one full-domain (or x-slab) single-level patch: three rotating f planes, five
+// stored high-order flux pairs and the low-order pair of stage 0.  Rows are x columns (slow), p is contiguous.  GX ghost columns per side.
 struct VrtSlabDev {
     int n_x, n_p;                // local interior columns, p cells
     int x_begin;                 // global finest index of local column 0
@@ -100,6 +98,7 @@ struct VrtSlabDev {
     double dx, dp;
     double* f[3];                // rotating: cur0 = f^n, cur1 = stage value, spare
     double* FxH[5]; double* FpH[5];   // one allocation, planes interleaved FxH[0], FpH[0], FxH[1], ... (one 3-D TMA box covers a stage's history)
+    double *FxL0, *FpL0;         // planes 10, 11 of the same allocation: the unscaled low-order flux pair of stage 0 (quirk Q1)
     double *chargeR, *currentR;  // n_x each
 };
 // TMA descriptors (CUtensorMap, 128 bytes each) of a slab's planes for the fused stage: [0] the three f planes with a
@@ -198,7 +197,6 @@ int vrt_fields_cfl(vrt_ctx* c);
 int vrt_fields_assemble_begin(vrt_ctx* c);
 int vrt_fields_assemble_add(vrt_ctx* c, int s, const double* chargeR, const double* currentR, int x0, int n);
 int vrt_fields_assemble_end(vrt_ctx* c);
-int vrt_fields_snapshot_stage0(vrt_ctx* c);
 int vrt_fields_neutralize(vrt_ctx* c);
 // fused path (vrt_fused.cu)
 int vrt_fused_stage(vrt_ctx* c, int s, const double* d_dt, int step);
