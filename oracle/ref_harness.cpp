@@ -24,6 +24,10 @@
 //     interp <lvl> <k> x0 p0 x1 p1 ...             interpRectanglesUp               -> "k x0 p0 x1 p1 ..."
 //     merge <lvl> x0 p0 x1 p1                      mergeDownFlaggedData             -> "n x p x p ..."
 //   The host build runs them without a Mesh and without a device (tests/test_host_clustering.py).
+//
+//        ref_harness settings out.txt nx np Lfinest [np_ion]
+//   prints what Settings derives from Input / Particles (Settings.cpp:5-195): level sizes and spacings, species constants, fMax,
+//   and the stage times of UpdateTime over two steps, as "name value" lines with 17 significant digits (no device needed).
 #include "veritas.hpp"
 #include "Settings.hpp"
 #include "SolverManager.hpp"
@@ -211,8 +215,46 @@ static int cluster_mode(int argc, char** argv) {
     return 0;
 }
 
+// Settings' derived quantities (see the usage comment)
+static int settings_mode(int argc, char** argv) {
+    if (argc < 6) { fprintf(stderr, "usage: %s settings out.txt nx np Lfinest [np_ion]\n", argv[0]); return 2; }
+    FILE* o = fopen(argv[2], "w");
+    if (!o) { perror(argv[2]); return 1; }
+    g_case.density = 0.1;
+    Input grid; Particles particles; Output output;
+    configure_case(atoi(argv[3]), atoi(argv[4]), argc > 6 ? atoi(argv[6]) : atoi(argv[4]), atoi(argv[5]), grid, particles);
+    output.time = output.rectangleData = output.charge = output.potential = output.EFieldLongitudinal =
+        output.EFieldTransverse = output.BFieldTransverse = output.AFieldSquared = output.energy = false;
+    Settings st(grid, particles, output);
+    auto P = [&](const std::string& name, double v) { fprintf(o, "%s %.17g\n", name.c_str(), v); };
+    P("maxDepth", st.maxDepth); P("refinementRatio", st.refinementRatio); P("x_size", st.x_size); P("x_size_finest", st.x_size_finest);
+    P("dx", st.dx); P("minEfficiency", st.minEfficiency); P("refinementCriteria", st.refinementCriteria); P("cfl", st.cfl);
+    P("sizeWeight", st.sizeWeight); P("quadratureDepth", st.quadratureDepth); P("preLength", st.preLength); P("postLength", st.postLength);
+    P("plasma_xl_bound", st.plasma_xl_bound); P("plasma_xr_bound", st.plasma_xr_bound);
+    P("tempEM0", st.tempEM[0]); P("tempEM1", st.tempEM[1]);
+    for (int l = 0; l <= st.maxDepth; l++) {
+        P("GetDx" + std::to_string(l), st.GetDx(l)); P("GetXSize" + std::to_string(l), st.GetXSize(l));
+        for (int s = 0; s < 2; s++) {
+            P("GetDp" + std::to_string(l) + "_" + std::to_string(s), st.GetDp(l, s));
+            P("GetPSize" + std::to_string(l) + "_" + std::to_string(s), st.GetPSize(l, s));
+        }
+    }
+    for (int s = 0; s < 2; s++) {
+        const std::string k = std::to_string(s);
+        P("m" + k, st.GetMass(s)); P("q" + k, st.GetCharge(s)); P("dp" + k, st.dp[s]); P("pmin" + k, st.pmin[s]);
+        P("p_size" + k, st.p_size[s]); P("p_size_finest" + k, st.p_size_finest[s]); P("temp0_" + k, st.temp[s][0]); P("temp1_" + k, st.temp[s][1]);
+        P("fMax" + k, st.GetfMax(s));
+    }
+    const double dts[2] = {1.25e-18, 3.0e-17};
+    for (int n = 0; n < 2; n++)
+        for (int i = 0; i < 6; i++) { st.UpdateTime(i, dts[n]); P("time_step" + std::to_string(n) + "_stage" + std::to_string(i), st.time); }
+    fclose(o);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc >= 2 && std::string(argv[1]) == "cluster") return cluster_mode(argc, argv);
+    if (argc >= 2 && std::string(argv[1]) == "settings") return settings_mode(argc, argv);
     if (argc < 7) { fprintf(stderr, "usage: %s out.bin nx np Lfinest density steps [key=value...]\n", argv[0]); return 2; }
     const char* out = argv[1];
     unsigned nx = atoi(argv[2]), np = atoi(argv[3]), Lfinest = atoi(argv[4]);

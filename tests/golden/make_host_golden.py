@@ -1,7 +1,10 @@
-"""Generate tests/golden/cluster_cases.txt / cluster_expected.txt: flag sets for the regrid clustering (Mesh.cpp:298-792) and what
+"""Generate the host-logic fixtures.  (1) tests/golden/cluster_cases.txt / cluster_expected.txt: flag sets for the regrid clustering (Mesh.cpp:298-792) and what
 the UNMODIFIED reference (oracle/_ref/ref_harness, `cluster` mode) makes of them.  Run in the build container:
 
-    python tests/golden/make_cluster_golden.py
+    python tests/golden/make_host_golden.py
+
+(2) tests/golden/settings/settings_<nx>_<np>_<Lfinest>[_<np_ion>].txt: what the reference's Settings derives for those sizes
+(`settings` mode of the harness), used by tests/test_host_settings.py.
 
 Deterministic (numpy RandomState(2017)).  The case kinds are described in oracle/ref_harness.cpp; the level sizes come from the
 harness arguments NX NP LFINEST below (coarsest 32 x 16, r = 2, three levels: 32x16, 64x32, 128x64).
@@ -87,6 +90,11 @@ def main():
     subprocess.check_call([HARNESS, "cluster", cases_path, exp_path, str(NX), str(NP), str(LFINEST)], stdout=subprocess.DEVNULL, env=env)
     n = sum(1 for _ in open(exp_path))
     print(f"{n} cases -> {exp_path} ({os.path.getsize(cases_path)} + {os.path.getsize(exp_path)} bytes)")
+    os.makedirs(os.path.join(OUT, "settings"), exist_ok=True)
+    for sizes in (("64", "32", "1"), ("32", "16", "3"), ("48", "32", "2", "16"), ("2048", "256", "1")):
+        path = os.path.join(OUT, "settings", "settings_" + "_".join(sizes) + ".txt")
+        subprocess.check_call([HARNESS, "settings", path] + list(sizes), stdout=subprocess.DEVNULL, env=env)
+        print(path)
 
 
 if __name__ == "__main__":

@@ -2,7 +2,7 @@
 getExtrema, computeSignatures, hasHole, identifyInflection, splitRectangle, interpRectanglesUp, mergeDownFlaggedData —
 the reference's Mesh.cpp:298-792) against what the unmodified reference makes of the same flag sets.
 
-tests/golden/cluster_cases.txt / cluster_expected.txt are written by tests/golden/make_cluster_golden.py from
+tests/golden/cluster_cases.txt / cluster_expected.txt are written by tests/golden/make_host_golden.py from
 oracle/_ref/ref_harness (`cluster` mode).  The host classes run the same cases through oracle/_ref/host_harness, which in this
 mode creates neither a Mesh nor a device context, so the test needs no GPU.
 """
@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 CASES = os.path.join(GOLDEN, "cluster_cases.txt")
 EXPECTED = os.path.join(GOLDEN, "cluster_expected.txt")
-SIZES = ["32", "16", "3"]           # coarsest nx, np, levels: as in make_cluster_golden.py
+SIZES = ["32", "16", "3"]           # coarsest nx, np, levels: as in make_host_golden.py
 
 
 def run_cluster(exe, tmp_path):
