@@ -101,6 +101,10 @@ int vrt_moments(vrt_ctx* ctx);
 /* Mesh::InterpolateRhoAndJToFinestMesh(charge, J) (Mesh.cpp:52-56) for species s: ADDS the species' charge and current on the finest
  * grid to the two host arrays (x_size_finest doubles each). */
 int vrt_moments_species(vrt_ctx* ctx, int s, double* charge_host, double* j_host);
+/* Rectangle::CalculateRhoAndJ (Rectangle.cpp:157-282) of one patch: its chargeR and currentR, n_x * r^depth doubles each (the
+ * patch's columns on the finest x grid), as Level::CollectRhoAndJ (Level.cpp:42-62) sums them into the level's arrays.  Recomputes
+ * the species' moments on the device and leaves the assembled charge / J (all species) as vrt_moments does. */
+int vrt_patch_moments(vrt_ctx* ctx, int s, int patch, double* charge_r_host, double* current_r_host);
 /* EMFieldSolver::EnforceChargeNeutralization (EMSolver.cpp:621-629). */
 int vrt_enforce_neutralization(vrt_ctx* ctx);
 /* EMFieldSolver::UpdatePotential (EMSolver.cpp:156-192): periodic 4th-order Poisson + Ex0 update.  The

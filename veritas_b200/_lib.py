@@ -67,6 +67,7 @@ SIGNATURES = {
     "vrt_push_boundary_c": (C.c_int, [C.c_void_p, C.c_int]),
     "vrt_level_push": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "vrt_moments_species": (C.c_int, [C.c_void_p, C.c_int, dbl_p, dbl_p]),
+    "vrt_patch_moments": (C.c_int, [C.c_void_p, C.c_int, C.c_int, dbl_p, dbl_p]),
     "vrt_field_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]),
     "vrt_cfl_bound": (C.c_int, [C.c_void_p, dbl_p]),
     "vrt_update_time": (C.c_double, [C.c_double, C.c_int, C.c_double]),

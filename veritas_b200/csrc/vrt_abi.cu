@@ -549,6 +549,28 @@ int vrt_moments_species(vrt_ctx* c, int s, double* charge_host, double* j_host) 
     return moments_impl(c);
 }
 
+// Rectangle::chargeR / currentR of one patch after Rectangle::CalculateRhoAndJ (what Level::CollectRhoAndJ reads, Level.cpp:42-62)
+int vrt_patch_moments(vrt_ctx* c, int s, int patch, double* charge_r_host, double* current_r_host) {
+    if (int r = ready_species(c, s)) return r;
+    if (!check(c, charge_r_host && current_r_host && patch >= 0 && patch < (int)c->S[s].desc.size(), "vrt_patch_moments: bad arguments")) return VRT_ERR_ARG;
+    if (!check(c, c->n_ranks == 1, "vrt_patch_moments: single-rank contexts only")) return VRT_ERR_STATE;
+    VrtSpeciesState& S = c->S[s];
+    // the species' moment kernels also rebuild charges[s] and J from this species alone (as in vrt_moments_species); the
+    // assembled state of all species is restored by a full vrt_moments afterwards
+    int r;
+    if ((r = vrt_fields_assemble_begin(c))) return r;
+    r = (S.path == VRT_PATH_FUSED) ? vrt_fused_moments(c, s) : vrt_split_moments(c, s);
+    if (r) return r;
+    const double *d_charge, *d_current;
+    size_t n;
+    if (S.path == VRT_PATH_FUSED) { d_charge = S.slab.chargeR; d_current = S.slab.currentR; n = (size_t)S.slab.n_x; }
+    else { const VrtPatchDev& P = S.patches[patch]; d_charge = P.chargeR; d_current = P.currentR; n = (size_t)P.n_x * P.rtb; }
+    VRT_CUDA(c, cudaMemcpyAsync(charge_r_host, d_charge, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    VRT_CUDA(c, cudaMemcpyAsync(current_r_host, d_current, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    VRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return moments_impl(c);
+}
+
 // Rectangle::CalculateEnergy (Rectangle.cpp:284-305): the patch's contribution to dN/dp on the finest p grid
 int vrt_patch_energy(vrt_ctx* c, int s, int patch, double* energy_host) {
     if (int r = ready_species(c, s)) return r;

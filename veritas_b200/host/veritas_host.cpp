@@ -304,6 +304,22 @@ void Level::PushData(int updateType, int val) {
     if (rectangles.empty()) return;
     settings.Check(vrt_level_push(settings.Gpu(), particleType, depth, updateType, val), "vrt_level_push");
 }
+// Level::CollectRhoAndJ (Level.cpp:42-62): Rectangle::CalculateRhoAndJ on the device (vrt_patch_moments fills chargeR, currentR),
+// level sum on the host in the reference's order.  SolverManager::Advance does not come through here: EMFieldSolver::AssembleRhoAndJ
+// is one device pass over all levels and species (vrt_moments).
+void Level::CollectRhoAndJ() {
+    chargeL.assign(settings.x_size_finest, 0.0);
+    currentL.assign(settings.x_size_finest, 0.0);
+    for (auto& r : rectangles) {
+        settings.Check(vrt_patch_moments(settings.Gpu(), particleType, r->patch_id, r->chargeR.data(), r->currentR.data()), "vrt_patch_moments");
+        const int shift = r->x_pos, rtb = (int)r->relativeToBottom;
+        for (size_t j = 0; j < r->chargeR.size(); j++) { chargeL[shift * rtb + j] += r->chargeR[j]; currentL[shift * rtb + j] += r->currentR[j]; }
+    }
+}
+void Level::InterpolateRhoAndJToFinestMesh(std::vector<double>& charge, std::vector<double>& J) {     // Level.cpp:19-29
+    CollectRhoAndJ();
+    for (unsigned int i = 0; i < settings.x_size_finest; i++) { charge[i] += chargeL[i]; J[i] += currentL[i]; }
+}
 // Level::CollectEnergy (Level.cpp:64-78): Rectangle::CalculateEnergy on the device (vrt_patch_energy), level sum on the host
 void Level::CollectEnergy() {
     energyL.assign(settings.p_size_finest[particleType], 0.0);
@@ -752,6 +768,13 @@ double EMFieldSolver::GetCellAverageASquared(int i) {
     i = std::min(std::max(i, 0), (int)x_size + n_prepad + n_postpad - 1);
     const double ay = Ay[Index(i, 1)], az = Az[Index(i, 1)];
     return (ay * ay) + (az * az);
+}
+// EMFieldSolver::GetMagneticForce (EMSolver.cpp:666-673): (A x B)_x of the stage values at plasma cell i
+double EMFieldSolver::GetMagneticForce(int i) {
+    SyncHost();
+    i += n_prepad;
+    i = std::min(std::max(i, 0), (int)x_size + n_prepad + n_postpad - 1);
+    return Az[Index(i, 1)] * By[Index(i, 1)] - Ay[Index(i, 1)] * Bz[Index(i, 1)];
 }
 // EMFieldSolver::GetEfield (EMSolver.cpp:137-154) from the mirrored potential
 double EMFieldSolver::GetEfield(int i) {

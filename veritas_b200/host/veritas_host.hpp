@@ -179,10 +179,12 @@ public:
     void GetDataFromSameLevel(const std::unique_ptr<Level>& level);
     void GetDataFromCoarserLevel(const std::unique_ptr<Level>& level);
     void GetDataFromCoarseNewLevel(const std::unique_ptr<Level>& level);
+    void CollectRhoAndJ();                                              // Level.cpp:42-62
+    void InterpolateRhoAndJToFinestMesh(std::vector<double>& charge, std::vector<double>& J);   // Level.cpp:19-29
     void CollectEnergy();                                               // Level.cpp:64-78
     void InterpolateEnergyToFinestMesh(std::vector<double>& energy);    // Level.cpp:31-40
 private:
-    std::vector<double> energyL;
+    std::vector<double> chargeL, currentL, energyL;
 };
 
 // ---- Mesh (Mesh.hpp:4-41): one species, hierarchy + regridding on the host ------------------------------------------------------
@@ -252,6 +254,7 @@ public:
     double GetASquared(int i);
     double GetEfield(int i);
     double GetCellAverageASquared(int i);
+    double GetMagneticForce(int i);                    // EMSolver.cpp:666-673
     double EstimateCFLBound();
     void EnforceChargeNeutralization();
     void DumpCharge();

@@ -81,6 +81,14 @@ class Context:
         self.call("vrt_patch_energy", s, patch, _p(out))
         return out
 
+    def patch_moments(self, s, patch):
+        """Rectangle::chargeR, currentR of one patch after CalculateRhoAndJ: n_x * r^depth values each"""
+        p = self.patches[s][patch]
+        n = p["n_x"] * 2 ** p.get("depth", 0)
+        charge, current = np.zeros(n), np.zeros(n)
+        self.call("vrt_patch_moments", s, patch, _p(charge), _p(current))
+        return charge, current
+
     def checkpoint_write(self, path):
         self.call("vrt_checkpoint_write", str(path).encode())
 
