@@ -551,8 +551,9 @@ int vrt_moments_species(vrt_ctx* c, int s, double* charge_host, double* j_host) 
 
 // Rectangle::chargeR / currentR of one patch after Rectangle::CalculateRhoAndJ (what Level::CollectRhoAndJ reads, Level.cpp:42-62)
 int vrt_patch_moments(vrt_ctx* c, int s, int patch, double* charge_r_host, double* current_r_host) {
-    if (int r = ready_species(c, s)) return r;
-    if (!check(c, charge_r_host && current_r_host && patch >= 0 && patch < (int)c->S[s].desc.size(), "vrt_patch_moments: bad arguments")) return VRT_ERR_ARG;
+    if (int r = ready(c)) return r;          // the closing vrt_moments needs every species' hierarchy
+    if (!check(c, s >= 0 && s < c->n_species && charge_r_host && current_r_host && patch >= 0 && patch < (int)c->S[s].desc.size(),
+               "vrt_patch_moments: bad arguments")) return VRT_ERR_ARG;
     if (!check(c, c->n_ranks == 1, "vrt_patch_moments: single-rank contexts only")) return VRT_ERR_STATE;
     VrtSpeciesState& S = c->S[s];
     // the species' moment kernels also rebuild charges[s] and J from this species alone (as in vrt_moments_species); the
