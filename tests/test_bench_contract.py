@@ -21,7 +21,7 @@ def test_reference_arm_json_line():
     assert d["higher_is_better"] is True and d["value"] > 1e5 and d["dtype"] == "f64"
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == d["value"] and "config 1" in cb["sample"]
+    assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample of config 3" in cb["sample"]
     assert d["gpu_launches"] == 0 and d["steps"] == 1 and d["warmup"] == 1
 
 
