@@ -113,7 +113,8 @@ def reference_arm(args, rank):
     kv = dict(x.split("=") for x in line.split()[1:])
     value = float(kv["cell_updates_per_s_per_stage"])
     sec = float(kv["advance_s"])
-    sample = f"{REF_SAMPLE_TEXT}; {steps} steps of SolverManager::Advance from t=3T, OMP_NUM_THREADS={cores}"
+    text = REF_SAMPLE_TEXT if args.gpus == 1 else REF_SAMPLE_TEXT.replace("sample of config 3: 2048 of its 65536", "sample of config 5: 2048 of its 262144")
+    sample = f"{text}; {steps} steps of SolverManager::Advance from t=3T, OMP_NUM_THREADS={cores}"
     print(json.dumps({
         "impl": "reference", "metric": "phase-space cell-updates/s per RK stage", "value": value, "unit": "cell-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / steps,
