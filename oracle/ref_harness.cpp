@@ -28,6 +28,12 @@
 //        ref_harness settings out.txt nx np Lfinest [np_ion]
 //   prints what Settings derives from Input / Particles (Settings.cpp:5-195): level sizes and spacings, species constants, fMax,
 //   and the stage times of UpdateTime over two steps, as "name value" lines with 17 significant digits (no device needed).
+//
+//        ref_harness transfer out.txt
+//   the host-side regrid data path on hand-made patches (no Mesh, no device): Rectangle::GetInterpolantsREF,
+//   GetDataFromCoarseLevelRectangle / GetDataFromSameLevelRectangle / GetDataFromCoarseNewLevelRectangle (Rectangle.cpp:892-941,
+//   1100-1128) from a coarse and an old fine patch into two new fine patches, and Rectangle::getError (866-890) on the coarse and
+//   on a new patch; prints the new patches' f and the flagged cells with 17 significant digits.
 #include "veritas.hpp"
 #include "Settings.hpp"
 #include "SolverManager.hpp"
@@ -35,6 +41,7 @@
 #include "Mesh.hpp"
 #include "Level.hpp"
 #include "Rectangle.hpp"
+#include "BoundaryCondition.hpp"
 #include "../veritas_b200/host/laser_plasma_case.hpp"
 #include <cstdio>
 #include <cstdlib>
@@ -252,7 +259,78 @@ static int settings_mode(int argc, char** argv) {
     return 0;
 }
 
+// host-side regrid data path on hand-made patches (see the usage comment)
+static int transfer_mode(int argc, char** argv) {
+    if (argc < 3) { fprintf(stderr, "usage: %s transfer out.txt\n", argv[0]); return 2; }
+    FILE* o = fopen(argv[2], "w");
+    if (!o) { perror(argv[2]); return 1; }
+    g_case.density = 0.1;
+    Input grid; Particles particles; Output output;
+    configure_case(32, 16, 16, 2, grid, particles);
+    output.time = output.rectangleData = output.charge = output.potential = output.EFieldLongitudinal =
+        output.EFieldTransverse = output.BFieldTransverse = output.AFieldSquared = output.energy = false;
+    Settings st(grid, particles, output);
+    st.refinementCriteria = 0.02;            // of the order of the test pattern's scaled differences: a non-trivial flag set
+    std::shared_ptr<Rectangle> bc = std::make_shared<BoundaryCondition>();
+    auto make = [&](int n_x, int n_p, int x_pos, int p_pos, int depth) {
+        return std::make_shared<Rectangle>(n_x, n_p, x_pos, p_pos, depth, st, bc, true, true, true, true, 0);
+    };
+    const double fm = st.GetfMax(0);
+    // smooth bump + ripple + floor in finest-grid units, different in states 0 and 1, ghost layers included
+    auto fill = [&](Rectangle& R, double shift) {
+        for (int i = -2; i < R.n_x + 2; i++)
+            for (int j = -2; j < R.n_p + 2; j++) {
+                const double X = (i + R.x_pos + 0.5) * R.relativeToBottom, P = (j + R.p_pos + 0.5) * R.relativeToBottom;
+                const double v = fm * (std::exp(-((X - 30 - shift) * (X - 30 - shift) / 80 + (P - 14) * (P - 14) / 20)) +
+                                       0.05 * std::sin(0.7 * X) * std::cos(0.9 * P) + 0.06);
+                R.f[R.Index3(i, j, 0)] = v;
+                R.f[R.Index3(i, j, 1)] = v * (1 + 0.01 * std::cos(X + shift));
+                R.f[R.Index3(i, j, 2)] = -v;
+            }
+    };
+    auto dump_f = [&](const char* name, Rectangle& R) {
+        fprintf(o, "%s %d %d %d %d\n", name, R.n_x, R.n_p, R.x_pos, R.p_pos);
+        for (int i = -2; i < R.n_x + 2; i++)
+            for (int j = -2; j < R.n_p + 2; j++)
+                fprintf(o, "%d %d %.17g %.17g %.17g\n", i, j, R.f[R.Index3(i, j, 0)], R.f[R.Index3(i, j, 1)], R.f[R.Index3(i, j, 2)]);
+    };
+    auto dump_flags = [&](const char* name, Rectangle& R) {
+        std::vector<coords> flagged;
+        R.getError(flagged, 0);
+        fprintf(o, "%s %zu", name, flagged.size());
+        for (const coords& c : flagged) fprintf(o, " %d %d", c.first, c.second);
+        fprintf(o, "\n");
+    };
+    auto coarse = make(32, 16, 0, 0, 1);          // the whole coarse level
+    auto old_fine = make(16, 8, 10, 6, 0);        // fine-level indices (64 x 32 grid)
+    auto new_a = make(24, 12, 8, 4, 0);           // overlaps old_fine: coarse interpolation, then same-level copy on the overlap
+    auto new_b = make(8, 8, 40, 16, 0);           // no old fine data: filled by the coarse-new pass alone
+    auto new_c = make(12, 8, 0, 24, 0);           // touches the domain corner: the coarse ring reaches into the ghost layers
+    fill(*coarse, 0.0); fill(*old_fine, 1.5);
+    const double five[3][5] = {{0.1, 0.4, 0.9, 0.5, 0.2}, {1.0, 1.0, 1.0, 1.0, 1.0}, {0.0, -0.3, 2.0, 0.7, 0.1}};
+    for (const double* v : {five[0], five[1], five[2]}) {
+        std::vector<double> sub = coarse->GetInterpolantsREF(v[0], v[1], v[2], v[3], v[4]);
+        fprintf(o, "interpolants %zu", sub.size());
+        for (double x : sub) fprintf(o, " %.17g", x);
+        fprintf(o, "\n");
+    }
+    // the order of Mesh::InterMeshDataTransfer (Mesh.cpp:116-130)
+    for (auto& target : {new_a, new_b, new_c}) coarse->GetDataFromCoarseLevelRectangle(target);
+    dump_f("after_coarse_a", *new_a);
+    for (auto& target : {new_a, new_b, new_c}) old_fine->GetDataFromSameLevelRectangle(target);
+    dump_f("after_same_a", *new_a);
+    auto fresh_b = make(8, 8, 40, 16, 0);
+    auto fresh_a = make(24, 12, 8, 4, 0);
+    old_fine->GetDataFromSameLevelRectangle(fresh_a);
+    for (auto& target : {fresh_a, fresh_b}) coarse->GetDataFromCoarseNewLevelRectangle(target);
+    dump_f("coarse_new_a", *fresh_a); dump_f("coarse_new_b", *fresh_b); dump_f("corner_c", *new_c);
+    dump_flags("flags_coarse", *coarse); dump_flags("flags_new_a", *new_a); dump_flags("flags_old_fine", *old_fine);
+    fclose(o);
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 2 && std::string(argv[1]) == "transfer") return transfer_mode(argc, argv);
     if (argc >= 2 && std::string(argv[1]) == "cluster") return cluster_mode(argc, argv);
     if (argc >= 2 && std::string(argv[1]) == "settings") return settings_mode(argc, argv);
     if (argc < 7) { fprintf(stderr, "usage: %s out.bin nx np Lfinest density steps [key=value...]\n", argv[0]); return 2; }

@@ -6,6 +6,9 @@ the UNMODIFIED reference (oracle/_ref/ref_harness, `cluster` mode) makes of them
 (2) tests/golden/settings/settings_<nx>_<np>_<Lfinest>[_<np_ion>].txt: what the reference's Settings derives for those sizes
 (`settings` mode of the harness), used by tests/test_host_settings.py.
 
+(3) tests/golden/host_transfer.txt: Rectangle::GetInterpolantsREF, the three old -> new patch transfers and Rectangle::getError on
+hand-made patches (`transfer` mode), used by tests/test_host_transfer.py.
+
 Deterministic (numpy RandomState(2017)).  The case kinds are described in oracle/ref_harness.cpp; the level sizes come from the
 harness arguments NX NP LFINEST below (coarsest 32 x 16, r = 2, three levels: 32x16, 64x32, 128x64).
 """
@@ -95,6 +98,10 @@ def main():
         path = os.path.join(OUT, "settings", "settings_" + "_".join(sizes) + ".txt")
         subprocess.check_call([HARNESS, "settings", path] + list(sizes), stdout=subprocess.DEVNULL, env=env)
         print(path)
+    # (3) host-side regrid data path on hand-made patches (`transfer` mode of the harness), tests/test_host_transfer.py
+    path = os.path.join(OUT, "host_transfer.txt")
+    subprocess.check_call([HARNESS, "transfer", path], stdout=subprocess.DEVNULL, env=env)
+    print(path)
 
 
 if __name__ == "__main__":
