@@ -33,7 +33,8 @@
 //   the host-side regrid data path on hand-made patches (no Mesh, no device): Rectangle::GetInterpolantsREF,
 //   GetDataFromCoarseLevelRectangle / GetDataFromSameLevelRectangle / GetDataFromCoarseNewLevelRectangle (Rectangle.cpp:892-941,
 //   1100-1128) from a coarse and an old fine patch into two new fine patches, and Rectangle::getError (866-890) on the coarse and
-//   on a new patch; prints the new patches' f and the flagged cells with 17 significant digits.
+//   on a new patch, and Rectangle::InitializeDistribution (616-669) on a coarse and a fine patch; prints the patches' f and the
+//   flagged cells with 17 significant digits.
 #include "veritas.hpp"
 #include "Settings.hpp"
 #include "SolverManager.hpp"
@@ -325,6 +326,12 @@ static int transfer_mode(int argc, char** argv) {
     for (auto& target : {fresh_a, fresh_b}) coarse->GetDataFromCoarseNewLevelRectangle(target);
     dump_f("coarse_new_a", *fresh_a); dump_f("coarse_new_b", *fresh_b); dump_f("corner_c", *new_c);
     dump_flags("flags_coarse", *coarse); dump_flags("flags_new_a", *new_a); dump_flags("flags_old_fine", *old_fine);
+    // Rectangle::InitializeDistribution (Rectangle.cpp:616-669): sub-cell quadrature of the user's initial distribution, on a coarse
+    // patch and on a fine patch across the plasma slab's left edge
+    auto init_coarse = make(32, 16, 0, 0, 1);
+    auto init_fine = make(16, 8, 14, 12, 0);
+    init_coarse->InitializeDistribution(); init_fine->InitializeDistribution();
+    dump_f("init_coarse", *init_coarse); dump_f("init_fine", *init_fine);
     fclose(o);
     return 0;
 }

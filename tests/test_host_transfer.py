@@ -1,7 +1,7 @@
 """Host logic on the CPU: the host-side regrid data path of the veritas_b200 host classes (the path VRT_HOST_REGRID=1 selects, and
 the reference's only one) — Rectangle::GetInterpolantsREF, GetWenoValueFromCoarseLevel, GetDataFromCoarseLevelRectangle,
 GetDataFromSameLevelRectangle, GetDataFromCoarseNewLevelRectangle (Rectangle.cpp:121-137, 343-415, 892-941, 1100-1128) and
-Rectangle::getError with ErrorEstimate (866-890, Rectangle.hpp:128-130) — on hand-made patches, bit for bit against the unmodified
+Rectangle::getError with ErrorEstimate (866-890, Rectangle.hpp:128-130), Rectangle::InitializeDistribution (616-669) — on hand-made patches, bit for bit against the unmodified
 reference (tests/golden/host_transfer.txt, written by oracle/_ref/ref_harness in `transfer` mode).  No Mesh, no device."""
 import os
 import subprocess
@@ -22,7 +22,7 @@ def run_transfer(exe, tmp_path):
 def test_host_transfer_and_error_flags_equal_reference_golden(tmp_path):
     assert os.path.exists(os.path.join(REF_DIR, "host_harness")), "oracle/_ref/host_harness missing: run __graft_entry__.build()"
     got, want = run_transfer("host_harness", tmp_path), open(EXPECTED).read().splitlines()
-    assert len(got) == len(want) > 1500
+    assert len(got) == len(want) > 2500
     bad = [(i, g, w) for i, (g, w) in enumerate(zip(got, want)) if g != w]
     assert not bad, bad[:5]
 
@@ -45,6 +45,9 @@ def test_transfer_fixture_is_not_trivial():
     assert sect["after_coarse_a"] != sect["after_same_a"]
     interior_b = [row for row in sect["coarse_new_b"] if row[0] != 0.0]
     assert len(interior_b) >= 8 * 8
+    # the initial distribution is a slab in x: some columns of the fine patch are empty, some are not
+    nz = [row for row in sect["init_fine"] if row[0] != 0.0]
+    assert 0 < len(nz) < 16 * 8 and any(row[0] != 0.0 for row in sect["init_coarse"])
 
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(REF_DIR, "ref_harness")), reason="reference harness not built")
