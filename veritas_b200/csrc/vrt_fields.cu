@@ -317,13 +317,14 @@ __global__ void k_neutralize(VrtFields F) {
     if (i < F.N) { F.J[i] = 0.0; F.neutral[i] = -F.charge[i]; }
 }
 
-bool g_tab_loaded = false;
+bool g_tab_loaded[64] = {};      // __constant__ memory is per device: one flag per device ordinal
 inline int grid1(int n, int b = 256) { return (n + b - 1) / b; }
 
 }  // namespace
 
 int vrt_fields_init_tables(vrt_ctx* c) {
-    if (!g_tab_loaded) { VRT_CUDA(c, cudaMemcpyToSymbol(c_tab, &kTableau, sizeof(VrtTableau))); g_tab_loaded = true; }
+    bool& loaded = g_tab_loaded[c->device & 63];
+    if (!loaded) { VRT_CUDA(c, cudaMemcpyToSymbol(c_tab, &kTableau, sizeof(VrtTableau))); loaded = true; }
     return 0;
 }
 

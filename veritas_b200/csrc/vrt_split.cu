@@ -10,7 +10,7 @@
 namespace {
 
 __constant__ VrtTableau c_tabs;
-bool g_tabs_loaded = false;
+bool g_tabs_loaded[64] = {};     // __constant__ memory is per device: one flag per device ordinal
 
 #define PATCH_THREAD_SETUP                                                       \
     const VrtPatchDev& P = patches[blockIdx.y];                                  \
@@ -274,7 +274,8 @@ int vrt_split_patch_energy(vrt_ctx* c, int s, int patch, double* host_energy) {
 }
 
 int vrt_split_init_tables(vrt_ctx* c) {
-    if (!g_tabs_loaded) { VRT_CUDA(c, cudaMemcpyToSymbol(c_tabs, &kTableau, sizeof(VrtTableau))); g_tabs_loaded = true; }
+    bool& loaded = g_tabs_loaded[c->device & 63];
+    if (!loaded) { VRT_CUDA(c, cudaMemcpyToSymbol(c_tabs, &kTableau, sizeof(VrtTableau))); loaded = true; }
     return 0;
 }
 
