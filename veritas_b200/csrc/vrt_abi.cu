@@ -733,10 +733,8 @@ int vrt_step(vrt_ctx* c, double dt, const double laser[12]) {
     const long l0 = c->launches;
     // The plane rotation of the fused path has period 2 after the first step; graphs are cached per rotation state.
     int key = 0;
-    bool any_fused = false;
-    for (auto& S : c->S) if (S.path == VRT_PATH_FUSED) { any_fused = true; key = S.i_f0; if (!check(c, S.i_f0 == S.i_f1, "vrt_step: mid-step state")) return VRT_ERR_STATE; }
+    for (auto& S : c->S) if (S.path == VRT_PATH_FUSED) { key = S.i_f0; if (!check(c, S.i_f0 == S.i_f1, "vrt_step: mid-step state")) return VRT_ERR_STATE; }
     for (auto& S : c->S) if (S.path == VRT_PATH_FUSED && !check(c, S.i_f0 == key, "vrt_step: species out of phase")) return VRT_ERR_STATE;
-    (void)any_fused;
     const bool use_graph = c->use_graph && c->n_ranks == 1;
     if (!use_graph) {
         if (int r = enqueue_step(c)) return r;
