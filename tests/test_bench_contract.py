@@ -32,3 +32,16 @@ def test_our_arm_needs_a_gpu():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
                        text=True, timeout=600)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/ref_harness not built (run __graft_entry__.build())")
+def test_reference_arm_under_torchrun_prints_once():
+    """launched as the driver launches N > 1: rank 0 alone runs and prints the line, the other ranks exit 0 without work"""
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29541", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["scaling"] == "strong" and "sample of config 5" in d["config"]["workload"]
