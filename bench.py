@@ -332,7 +332,7 @@ def main():
         raise SystemExit(f"bench.py: state is not finite / particle number drifted ({drift}); the measurement is void")
 
     if rank == 0:
-        cb = None if args.no_cpu_baseline else cpu_baseline()
+        cb = None if (args.no_cpu_baseline or n_gpus > 1) else cpu_baseline()     # the CPU baseline is timed at N = 1 only
         out = {
             "metric": "phase-space cell-updates/s per RK stage", "value": value, "unit": "cell-updates/s", "n_gpus": n_gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
