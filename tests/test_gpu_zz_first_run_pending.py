@@ -1,10 +1,11 @@
-"""Per-patch moments at the ABI (vrt_patch_moments = Rectangle::chargeR / currentR after CalculateRhoAndJ, what
+"""First-run-pending GPU tests.  (1) Per-patch moments at the ABI (vrt_patch_moments = Rectangle::chargeR / currentR after CalculateRhoAndJ, what
 Level::CollectRhoAndJ sums, Level.cpp:42-62): the level sums of the patches must reproduce the species' charge and the total
 current that vrt_moments assembles, on a 3-level hierarchy from the reference's regrid (split path) and on the single-patch fused
 path, and the assembled state must be left as vrt_moments leaves it.
 
 Written after round 1's GPU budget was spent, so its first run on a B200 is the driver's: it is marked xfail(strict=False) until
-it has been seen green once, and sorts last so that it cannot mask another test."""
+it has been seen green once, and sorts last so that it cannot mask another test.  (2) The shipped five-level case through the host
+classes against the reference (same status)."""
 import numpy as np
 import pytest
 
@@ -75,3 +76,13 @@ def test_patch_moments_fused_path():
     ctx.load_reference_state(d, "step0")
     check(ctx, mt["nx"])
     ctx.close()
+
+
+def test_shipped_five_level_case_through_host_classes(tmp_path):
+    """The reference's shipped configuration (veritas.cpp:7-35: coarse 76 x 150 / 76 x 50, five levels, overdense n = 2 N_c) through
+    both builds of the harness, free-running over two regrids: identical hierarchies, f and fields within tolerance.  The other
+    AMR parity cases stop at three levels."""
+    from test_gpu_host_layer import run_both, compare
+    ref, host = run_both(tmp_path, ["76", "150", "5", "2.0", "6", "np_ion=50", "regrid_every=3", "threads=4"])
+    worst, most = compare(ref, host, 6, 1e-9, 1e-12)
+    print("shipped 5-level case, 6 free-running steps, regrid every 3: worst relative L2", {k: "%.2e" % v for k, v in worst.items()})
