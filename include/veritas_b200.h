@@ -135,6 +135,12 @@ int vrt_step_fields(vrt_ctx* ctx, double dt, const double laser[12]);
 /* number of kernels the last vrt_step / vrt_step_fields launched (for bench.py's gpu_launches) */
 long vrt_last_step_launches(const vrt_ctx* ctx);
 
+/* Diagnostic (no reference counterpart): the launch plan the fused streaming path uses for species s, so that a test can assert
+ * which kernel specialisations a mesh exercises.  out[0] = CTA width W (threads; 128 = the compile-time-width instance),
+ * out[1] = p strips, out[2] = x chunks, out[3] = CTAs taking the interior specialisation (no boundary predicates),
+ * out[4], out[5] = cells per thread and threads per CTA of the streaming moments kernel (k_slab_moments<CPT, NT, .>). */
+int vrt_fused_plan(vrt_ctx* ctx, int s, int out[6]);
+
 /* option 0: replay vrt_step through a captured CUDA graph (default 1) or launch kernel by kernel (0);
  * option 1: run the species' Vlasov stages of one RK stage on concurrent streams / graph branches (default 1) */
 int vrt_set_option(vrt_ctx* ctx, int option, int value);

@@ -17,6 +17,11 @@
 //   keys: dump_every=1 stage_dumps=0 regrid_every=0 threads=N refine_mode=0 tail_p0=2 pre_steps=-1
 //         time_only=0 internals=0 a0=1 file_output=0 (every N steps: SolverManager::fileOutput + OutputRectangles into
 //         ./output, which must exist with its rectangleData subdirectory) precision=15 energy=0 (dN/dp dump; use threads=1)
+//         compact=0 (1: per patch only state 1 of f, as record ".../f1" — at a step boundary states 0 and 1 coincide,
+//         Rectangle.cpp:1614-1622 — a third of the dump size for the large per-step parity cases)
+//         patch_moments=0 (1, reference build only: before every dump run EMFieldSolver::AssembleRhoAndJ on the dumped state and
+//         add each patch's Rectangle::chargeR / currentR, what Level::CollectRhoAndJ sums, Level.cpp:42-62; the dumped charge /
+//         J / charges are then the moments of that state, which the next Advance recomputes at its stage 0 anyway)
 //
 //        ref_harness cluster cases.txt out.txt nx np Lfinest
 //   runs the regrid clustering members of Mesh (Mesh.cpp:298-792) on the flag sets of cases.txt, one case per line:
@@ -86,9 +91,12 @@ static void put(const std::string& name, const double* data, std::initializer_li
 }
 static void put1(const std::string& name, double v) { put(name, &v, {1}); }
 
+static bool g_compact = false, g_patch_moments = false;
 static void dump_state(SolverManager& SM, Settings& st, const std::string& tag, bool internals) {
 #ifdef VRT_HOST_BUILD
     SM.SyncHost();     // veritas_b200 host classes: Rectangle::f and the EMFieldSolver arrays are mirrors of device data
+#else
+    if (g_patch_moments) SM.EMSolver->AssembleRhoAndJ();
 #endif
     EMFieldSolver& em = *SM.EMSolver;
     long M = em.x_size + em.n_prepad + em.n_postpad, N = em.x_size;
@@ -113,8 +121,18 @@ static void dump_state(SolverManager& SM, Settings& st, const std::string& tag, 
                 double desc[10] = {(double)R.n_x, (double)R.n_p, (double)R.x_pos, (double)R.p_pos, (double)R.depth,
                                    (double)R.up, (double)R.down, (double)R.left, (double)R.right, R.relativeToBottom};
                 put(p + "/desc", desc, {10});
-                put(p + "/f", R.f.data(), {R.n_x + 4, R.n_p + 4, 3});
+                if (g_compact) {
+                    std::vector<double> f1((size_t)(R.n_x + 4) * (R.n_p + 4));
+                    for (size_t c = 0; c < f1.size(); c++) f1[c] = R.f[3 * c + 1];
+                    put(p + "/f1", f1.data(), {R.n_x + 4, R.n_p + 4});
+                } else {
+                    put(p + "/f", R.f.data(), {R.n_x + 4, R.n_p + 4, 3});
+                }
 #ifndef VRT_HOST_BUILD
+                if (g_patch_moments) {
+                    put(p + "/chargeR", R.chargeR.data(), {(long)R.chargeR.size()});
+                    put(p + "/currentR", R.currentR.data(), {(long)R.currentR.size()});
+                }
                 if (internals) {
                     put(p + "/FxH", R.FxH.data(), {R.n_x + 4, R.n_p + 4, 6});
                     put(p + "/FpH", R.FpH.data(), {R.n_x + 4, R.n_p + 4, 6});
@@ -348,7 +366,7 @@ int main(int argc, char** argv) {
     std::map<std::string, double> kv = {{"dump_every", 1}, {"stage_dumps", 0}, {"regrid_every", 0}, {"threads", 0},
                                         {"refine_mode", 0}, {"tail_p0", 2}, {"pre_steps", -1}, {"time_only", 0},
                                         {"internals", 0}, {"a0", 1}, {"np_ion", 0},
-                                        {"file_output", 0}, {"precision", 15}, {"energy", 0}};
+                                        {"file_output", 0}, {"precision", 15}, {"energy", 0}, {"compact", 0}, {"patch_moments", 0}};
     for (int i = 7; i < argc; i++) {
         std::string a = argv[i]; size_t e = a.find('=');
         if (e == std::string::npos || !kv.count(a.substr(0, e))) { fprintf(stderr, "bad arg %s\n", argv[i]); return 2; }
@@ -357,6 +375,7 @@ int main(int argc, char** argv) {
     g_case.refine_mode = (int)kv["refine_mode"]; g_case.tail_p0 = kv["tail_p0"]; g_case.a0 = kv["a0"];
     if (kv["threads"] > 0) omp_set_num_threads((int)kv["threads"]);
     bool time_only = kv["time_only"] != 0, internals = kv["internals"] != 0;
+    g_compact = kv["compact"] != 0; g_patch_moments = kv["patch_moments"] != 0;
 
     Input grid; Particles particles; Output output;
     unsigned np_ion = kv["np_ion"] > 0 ? (unsigned)kv["np_ion"] : np;

@@ -100,6 +100,15 @@ def test_host_layer_two_level_tail_regrid(tmp_path):
     print("2 levels (tail), regrid every 3 steps, 7 free-running steps: worst relative L2", {k: "%.2e" % v for k, v in worst.items()}, "max patches/level", most)
 
 
+def test_shipped_five_level_case_through_host_classes(tmp_path):
+    """The reference's shipped configuration (veritas.cpp:7-35: coarse 76 x 150 / 76 x 50, five levels, overdense n = 2 N_c) through
+    both builds of the harness, free-running over two regrids: identical hierarchies, f and fields within tolerance.  The other
+    AMR parity cases stop at three levels."""
+    ref, host = run_both(tmp_path, ["76", "150", "5", "2.0", "6", "np_ion=50", "regrid_every=3", "threads=4"])
+    worst, most = compare(ref, host, 6, 1e-9, 1e-12)
+    print("shipped 5-level case, 6 free-running steps, regrid every 3: worst relative L2", {k: "%.2e" % v for k, v in worst.items()})
+
+
 def _tokens(path):
     return [line.split() for line in open(path).read().splitlines()]
 

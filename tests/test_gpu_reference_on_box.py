@@ -31,10 +31,13 @@ def run_reference(tmp_path, args):
     r = subprocess.run([REF, path] + args, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:]
     rec = read_dump(path)
+    os.remove(path)
     out = {}
     for k, v in rec.items():       # Rectangle::f is AoS [cell][3 states]
         if k.endswith("/f"):
             out[k + "0"] = v[:, :, 0].copy(); out[k + "1"] = v[:, :, 1].copy()
+        elif k.endswith("/f1"):    # compact=1 dumps: state 1 only; at a step boundary state 0 is the same (Rectangle.cpp:1614-1622)
+            out[k] = v; out[k[:-1] + "0"] = v
         else:
             out[k] = v
     return out
@@ -48,10 +51,19 @@ def stage_lasers(L, laser, t, dt):
     return out, t
 
 
-def per_step_parity(d, steps, path=S.PATH_FUSED):
+TOL_MOMENTS = 1e-11     # rho_s, J: the p-reduction order differs from the reference's serial loop
+TOL_PHI = 1e-9          # PHI: quasi-neutral cancellation + the reference's dense LU round-off; measured value printed
+
+
+def per_step_parity(d, steps, path=S.PATH_FUSED, expect_plan=None):
     """Protocol P1: from every reference state one full step on the GPU, compared with the reference's next
-    state.  Returns the worst relative L2 per quantity."""
+    state: f and the transverse fields within 1e-12, the species' charge densities and J (the moments the last stage
+    assembled, EMSolver.cpp:104-122) within 1e-11, PHI within 1e-9.  Returns the worst relative L2 per quantity."""
     ctx, mt = make_ctx(d, path)
+    if expect_plan is not None:
+        for s in range(2):
+            plan = ctx.fused_plan(s)
+            expect_plan(plan)
     laser, L = laser_fn(mt), vb.load()
     worst = {}
     for n in range(1, steps + 1):
@@ -69,7 +81,13 @@ def per_step_parity(d, steps, path=S.PATH_FUSED):
             e = rel_l2(ctx.download_field(w, 0), d[f"step{n}/{k}"][0])
             worst[k] = max(worst.get(k, 0.0), e)
             assert e < TOL, (n, k, e)
-        worst["PHI"] = max(worst.get("PHI", 0.0), rel_l2(ctx.get_1d(S.PHI), d[f"step{n}/PHI"]))
+        for which, k in ((S.CHARGES0, "charges0"), (S.CHARGES0 + 1, "charges1"), (S.J, "J")):
+            e = rel_l2(ctx.get_1d(which), d[f"step{n}/{k}"])
+            worst[k] = max(worst.get(k, 0.0), e)
+            assert e < TOL_MOMENTS, (n, k, e)
+        e = rel_l2(ctx.get_1d(S.PHI), d[f"step{n}/PHI"])
+        worst["PHI"] = max(worst.get("PHI", 0.0), e)
+        assert e < TOL_PHI, (n, "PHI", e)
     ctx.close()
     return worst
 
@@ -104,11 +122,30 @@ def test_hundred_steps_per_step_parity_and_conservation(tmp_path):
     ctx.close()
 
 
-def test_config1_full_size_per_step_parity(tmp_path):
-    """BASELINE.json configs[0] at its full size (2048 x 256, single level, two species): 3 steps, protocol P1."""
-    d = run_reference(tmp_path, ["2048", "256", "1", "0.1", "3", "threads=0"])
-    worst = per_step_parity(d, 3)
-    print("config 1 (2048x256), per-step parity (worst relative L2):", {k: "%.2e" % v for k, v in worst.items()})
+def test_config1_full_size_hundred_steps_per_step_parity(tmp_path):
+    """BASELINE.json configs[0] at its full size (2048 x 256, single level, two species, underdense): the north_star criterion
+    itself — 100 steps of the reference's driver loop from t = 3T (veritas.cpp:135-144), protocol P1 on every one of them
+    (Rectangle.cpp:1255-1623 is the body compared)."""
+    d = run_reference(tmp_path, ["2048", "256", "1", "0.1", "100", "compact=1", "threads=0"])
+    worst = per_step_parity(d, 100)
+    print("config 1 (2048x256), 100 steps, per-step parity (worst relative L2):", {k: "%.2e" % v for k, v in worst.items()})
+
+
+@pytest.mark.parametrize("nx", [256, 2048])
+def test_benchmark_p_grid_per_step_parity(tmp_path, nx):
+    """The bench's own p grid (config 3: n_p = 4096 per species -> 34 strips of the 128-thread stage kernel, its interior
+    specialisation k_fused_stage<S, 4, 128> without boundary predicates, and the long-column moments kernel
+    k_slab_moments<33, 128, .>) against the reference, which can hold 256 and 2048 of config 3's 65536 columns: two species,
+    n = 0.1 N_c, the pulse inside the slab (t = 5T), 5 steps, protocol P1."""
+    d = run_reference(tmp_path, [str(nx), "4096", "1", "0.1", "5", "pre_steps=2000", "compact=1", "threads=0"])
+
+    def expect(plan):
+        assert plan["W"] == 128 and plan["strips"] == 34 and plan["interior_ctas"] >= 32 * (plan["chunks"] - 2) > 0, plan
+        assert (plan["moments_cpt"], plan["moments_threads"]) == (33, 128), plan
+
+    worst = per_step_parity(d, 5, expect_plan=expect)
+    assert float(np.abs(d["step0/a_squared"]).max()) > 0
+    print(f"{nx}x4096 (config 3's p grid), 5 steps, per-step parity (worst relative L2):", {k: "%.2e" % v for k, v in worst.items()})
 
 
 def test_config2_and_config4_full_size_free_running(tmp_path):
@@ -132,6 +169,71 @@ def test_config2_and_config4_full_size_free_running(tmp_path):
         worst = {k: max(worst[k], w[k]) for k in worst}
     hier = [len(h) for h in __import__("oracle.port", fromlist=["x"]).hierarchy_from_dump(ref, "step24")]
     print("config 4 (512x64, 3 levels, regrid at step 22), 24 free-running steps, patches per species", hier, {k: "%.2e" % v for k, v in worst.items()})
+
+
+def amr_per_step_parity(d, steps):
+    """Protocol P1 on the reference's own hierarchies (split path): from every reference state one full step on the GPU against
+    the reference's next state, f of every patch incl. ghost layers and the transverse fields within 1e-12.  Where the reference
+    regridded after the step (SolverManager::reGrid, veritas.cpp:146-151), the GPU follows with Mesh::InterMeshDataTransfer on the
+    device (vrt_regrid onto the reference's new hierarchy) + PushData + the commit of promoteHierarchyToMesh (Mesh.cpp:863-874),
+    so the comparison crosses the regrid on identical hierarchies."""
+    from oracle.port import hierarchy_from_dump
+    from test_gpu_amr import new_ctx, set_hierarchy, strip
+    mt = meta(d)
+    ctx = new_ctx(d, mt)
+    laser, L = laser_fn(mt), vb.load()
+    current, keys, worst, regrids, most = None, None, {}, 0, 0
+    for n in range(1, steps + 1):
+        H, Hn = hierarchy_from_dump(d, f"step{n - 1}"), hierarchy_from_dump(d, f"step{n}")
+        if current != strip(H):
+            keys = set_hierarchy(ctx, H)
+            current = strip(H)
+        most = max(most, sum(len(h) for h in H))
+        ctx.load_reference_state(d, f"step{n - 1}", keys)
+        dt = float(d[f"step{n}/dt"][0])
+        lasers, _ = stage_lasers(L, laser, float(d[f"step{n - 1}/time"][0]), dt)
+        ctx.step(dt, lasers)
+        if strip(Hn) != strip(H):
+            for s in range(2):
+                ctx.regrid(s, Hn[s]); ctx.push_data(s, 1); ctx.commit_state(s)
+            keys = [[p["key"] for p in h] for h in Hn]
+            current = strip(Hn)
+            regrids += 1
+        for s in range(2):
+            for p, k in enumerate(keys[s]):
+                e = rel_l2(ctx.download_f(s, p, 1), d[f"step{n}/{k}/f1"])
+                worst["f"] = max(worst.get("f", 0.0), e)
+                assert e < TOL, (n, k, e)
+        for w, k in enumerate(S.FIELD_NAMES):
+            e = rel_l2(ctx.download_field(w, 0), d[f"step{n}/{k}"][0])
+            worst[k] = max(worst.get(k, 0.0), e)
+            assert e < TOL, (n, k, e)
+        for which, k in ((S.CHARGES0, "charges0"), (S.CHARGES0 + 1, "charges1"), (S.J, "J")):
+            e = rel_l2(ctx.get_1d(which), d[f"step{n}/{k}"])
+            worst[k] = max(worst.get(k, 0.0), e)
+            assert e < TOL_MOMENTS, (n, k, e)
+        e = rel_l2(ctx.get_1d(S.PHI), d[f"step{n}/PHI"])
+        worst["PHI"] = max(worst.get("PHI", 0.0), e)
+        assert e < TOL_PHI, (n, "PHI", e)
+    ctx.close()
+    return worst, regrids, most
+
+
+def test_config2_full_size_per_step_parity_across_regrid(tmp_path):
+    """BASELINE.json configs[1] at full size (1024 x 128 coarse mesh, 2 levels, refinement forced into the high-momentum tail):
+    24 steps with the regrid after step 22, protocol P1 on every step."""
+    d = run_reference(tmp_path, ["1024", "128", "2", "0.1", "24", "refine_mode=1", "tail_p0=2", "regrid_every=22", "compact=1", "threads=0"])
+    worst, regrids, most = amr_per_step_parity(d, 24)
+    print("config 2 (1024x128 coarse, 2 levels), 24 steps per-step, regrids crossed", regrids, "patches", most, {k: "%.2e" % v for k, v in worst.items()})
+
+
+def test_config4_full_size_per_step_parity_across_regrid(tmp_path):
+    """BASELINE.json configs[3] at full size (512 x 64 coarse mesh, 3 levels, regrid every 22 steps as veritas.cpp:146-151):
+    24 steps, protocol P1 on every step, crossing the regrid."""
+    d = run_reference(tmp_path, ["512", "64", "3", "0.1", "24", "regrid_every=22", "compact=1", "threads=0"])
+    worst, regrids, most = amr_per_step_parity(d, 24)
+    assert regrids >= 1
+    print("config 4 (512x64 coarse, 3 levels), 24 steps per-step, regrids crossed", regrids, "patches", most, {k: "%.2e" % v for k, v in worst.items()})
 
 
 def compare_tag(ref, host, tag, tol_f=1e-10, tol_fields=1e-12):

@@ -74,6 +74,7 @@ SIGNATURES = {
     "vrt_step": (C.c_int, [C.c_void_p, C.c_double, dbl_p]),
     "vrt_step_fields": (C.c_int, [C.c_void_p, C.c_double, dbl_p]),
     "vrt_last_step_launches": (C.c_long, [C.c_void_p]),
+    "vrt_fused_plan": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "vrt_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "vrt_init_maxwellian_slab": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]),
     "vrt_set_slab": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),

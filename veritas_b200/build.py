@@ -22,7 +22,7 @@ UNITS = [
     ("vrt_split.cu", ["-fmad=false"]),
     ("vrt_amr.cu", ["-fmad=false"]),
     ("vrt_fused.cu", []),
-    ("vrt_init.cu", []),
+    ("vrt_init.cu", ["-fmad=false"]),
     ("vrt_comm.cu", []),
     ("vrt_checkpoint.cu", []),
 ]

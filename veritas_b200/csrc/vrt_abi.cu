@@ -776,6 +776,12 @@ int vrt_step_fields(vrt_ctx* c, double dt, const double laser[12]) {
 
 long vrt_last_step_launches(const vrt_ctx* c) { return c ? c->last_step_launches : 0; }
 
+int vrt_fused_plan(vrt_ctx* c, int s, int out[6]) {
+    if (int r = ready_species(c, s)) return r;
+    if (!check(c, out && c->S[s].path == VRT_PATH_FUSED, "vrt_fused_plan: species is not on the fused path")) return VRT_ERR_STATE;
+    return vrt_fused_plan_impl(c, s, out);
+}
+
 int vrt_set_option(vrt_ctx* c, int option, int value) {
     if (!c) return VRT_ERR_ARG;
     if (option == 0) { c->use_graph = value != 0; return 0; }

@@ -1,22 +1,24 @@
 // Rectangle::InitializeDistribution (Rectangle.cpp:616-665) on the device for the shipped Maxwellian slab
 // (Settings::InitialDistribution, veritas.cpp:107-115): sub-cell midpoint quadrature, nvals = r^(depth+quadratureDepth)
-// points per direction.  SURVEY.md §8(f) item 2 ("next"): lets large meshes start without a host pass.  Device exp()
-// differs from libm's by <= 1 ulp, so this is not bit-identical to a host-initialised run; parity tests upload
-// oracle states instead.
+// points per direction.  SURVEY.md §8(f) item 2 ("next"): lets large meshes start without a host pass.  The quadrature points
+// are formed in the reference's association — ((0.5 + k)/nvals + i + x_pos)·dx and Momentum((0.5 + l)/nvals + j) =
+// pmin + dp·(((0.5 + l)/nvals + j) + p_pos) (Rectangle.cpp:652-653, Rectangle.hpp:86-88) — and this unit is compiled with
+// -fmad=false, so the only difference to a host-initialised run is device exp() vs libm's (<= 1 ulp);
+// tests/test_gpu_initial_condition.py compares with the reference's step-0 state.
 #include "vrt_internal.cuh"
 #include <cmath>
 
 namespace {
 #define VRT_DPI 6.28318530718   // veritas.hpp:29
 
-__device__ double cell_average(double x_cell, double dx, double pmin, double dp, double jpos, int nvals, double xl, double xr, double n0, double T) {
+__device__ double cell_average(int i, int x_pos, double dx, double pmin, double dp, int j, int p_pos, int nvals, double xl, double xr, double n0, double T) {
     double temp = 0.0;
     const double norm = sqrt(VRT_DPI * T);
     for (int k = 0; k < nvals; k++) {
-        double xp = ((0.5 + k) / nvals + x_cell) * dx;
+        double xp = ((0.5 + k) / nvals + i + x_pos) * dx;
         double ne = ((xp > xl) && (xp < xr)) ? n0 : 0.0;
         for (int l = 0; l < nvals; l++) {
-            double pp = pmin + dp * ((0.5 + l) / nvals + jpos);
+            double pp = pmin + dp * (((0.5 + l) / nvals + j) + p_pos);
             temp += ne * exp(-(pp * pp) / (2.0 * T)) / norm;
         }
     }
@@ -28,7 +30,7 @@ __global__ void k_init_patch(VrtPatchDev P, double pmin, int nvals, double xl, d
     if (c >= P.npad) return;
     int i = (int)(c / P.pitch) - 2, j = (int)(c % P.pitch) - 2;
     if (i < 0 || i >= P.n_x || j < 0 || j >= P.n_p) return;
-    double v = cell_average((double)(i + P.x_pos), P.dx, pmin, P.dp, (double)(j + P.p_pos), nvals, xl, xr, n0, T);
+    double v = cell_average(i, P.x_pos, P.dx, pmin, P.dp, j, P.p_pos, nvals, xl, xr, n0, T);
     P.f0[c] = v; P.f1[c] = v;
 }
 
@@ -39,7 +41,7 @@ __global__ void k_init_slab(VrtSlabDev L, double* plane, double pmin, int nvals,
     int cl = (int)(idx / L.n_p) - L.gx, j = (int)(idx % L.n_p);
     int gi = L.x_begin + cl;
     if (gi < 0 || gi >= L.n_x_global) return;   // physical ghost columns stay 0
-    plane[(long)(cl + L.gx) * L.pitch + VRT_SLAB_GH + j] = cell_average((double)gi, L.dx, pmin, L.dp, (double)j, nvals, xl, xr, n0, T);
+    plane[(long)(cl + L.gx) * L.pitch + VRT_SLAB_GH + j] = cell_average(gi, 0, L.dx, pmin, L.dp, j, 0, nvals, xl, xr, n0, T);
 }
 }  // namespace
 

@@ -203,3 +203,4 @@ int vrt_fused_stage(vrt_ctx* c, int s, const double* d_dt, int step);
 int vrt_fused_moments(vrt_ctx* c, int s);
 int vrt_fused_zero_ghosts(vrt_ctx* c, int s, int plane_idx);
 int vrt_fused_make_maps(vrt_ctx* c, int s);
+int vrt_fused_plan_impl(vrt_ctx* c, int s, int out[6]);

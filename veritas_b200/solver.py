@@ -100,6 +100,18 @@ class Context:
             for s, ps in enumerate(patches):
                 self.patches[s] = [{k: p[k] for k in DESC_KEYS} for p in ps]
 
+    def regrid(self, s, patches):
+        """vrt_regrid: Mesh::InterMeshDataTransfer between the resident hierarchy and `patches` on the device"""
+        patches = [{k: p[k] for k in DESC_KEYS} for p in patches]
+        arr = (PatchDesc * len(patches))(*[PatchDesc(**p) for p in patches])
+        self.call("vrt_regrid", s, len(patches), arr)
+        self.patches[s] = patches
+
+    def fused_plan(self, s):
+        out = (C.c_int * 6)()
+        self.call("vrt_fused_plan", s, out)
+        return dict(W=out[0], strips=out[1], chunks=out[2], interior_ctas=out[3], moments_cpt=out[4], moments_threads=out[5])
+
     def get_path(self, s):
         return self.L.vrt_get_path(self.h, s)
 
