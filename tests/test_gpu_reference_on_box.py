@@ -52,7 +52,13 @@ def stage_lasers(L, laser, t, dt):
 
 
 TOL_MOMENTS = 1e-11     # rho_s, J: the p-reduction order differs from the reference's serial loop
-TOL_PHI = 1e-9          # PHI: quasi-neutral cancellation + the reference's dense LU round-off; measured value printed
+# PHI, two bounds.  (1) The solver alone — UpdatePotential on the reference's own assembled charge of that stage against the
+# reference's dense LU (EMSolver.cpp:156-192): 1e-9.  (2) End to end, PHI from the GPU's own moments: the right-hand side
+# rho_e + rho_i + rho_neutral is a difference of sums that cancel to ~1e-9 of either species in the quasi-neutral slab (exactly 0 at
+# t = 3T), so species charges that agree with the reference to 1e-17 still leave PHI reproducible only to ~1e-8 of its
+# (tiny) norm in the first steps; measured floor 6.9e-9 (2048 x 4096, step 1), bound 5e-8, worst value printed by every test.
+TOL_PHI_SOLVER = 1e-9
+TOL_PHI = 5e-8
 
 
 def per_step_parity(d, steps, path=S.PATH_FUSED, expect_plan=None):
@@ -88,6 +94,11 @@ def per_step_parity(d, steps, path=S.PATH_FUSED, expect_plan=None):
         e = rel_l2(ctx.get_1d(S.PHI), d[f"step{n}/PHI"])
         worst["PHI"] = max(worst.get("PHI", 0.0), e)
         assert e < TOL_PHI, (n, "PHI", e)
+        ctx.set_1d(S.CHARGE, d[f"step{n}/charge"])         # the solver alone: the reference's charge of the last stage -> PHI
+        ctx.poisson()
+        e = rel_l2(ctx.get_1d(S.PHI), d[f"step{n}/PHI"])
+        worst["PHI_solver"] = max(worst.get("PHI_solver", 0.0), e)
+        assert e < TOL_PHI_SOLVER, (n, "PHI from the reference's charge", e)
     ctx.close()
     return worst
 
@@ -215,6 +226,11 @@ def amr_per_step_parity(d, steps):
         e = rel_l2(ctx.get_1d(S.PHI), d[f"step{n}/PHI"])
         worst["PHI"] = max(worst.get("PHI", 0.0), e)
         assert e < TOL_PHI, (n, "PHI", e)
+        ctx.set_1d(S.CHARGE, d[f"step{n}/charge"])         # the solver alone: the reference's charge of the last stage -> PHI
+        ctx.poisson()
+        e = rel_l2(ctx.get_1d(S.PHI), d[f"step{n}/PHI"])
+        worst["PHI_solver"] = max(worst.get("PHI_solver", 0.0), e)
+        assert e < TOL_PHI_SOLVER, (n, "PHI from the reference's charge", e)
     ctx.close()
     return worst, regrids, most
 

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <stdexcept>
 
 int vrt_fields_refresh_efield(vrt_ctx* c);
 int vrt_init_kernels_maxwellian(vrt_ctx* c, int s, double xl, double xr, double n0, double T, int quadrature_depth);
@@ -175,7 +176,7 @@ int vrt_set_slab(vrt_ctx* c, int rank, int n_ranks, int x_begin, int x_end) {
 }
 
 // split path storage of one species: SoA planes per patch in the reference's padded layout, the device patch table grouped
-// by depth, and the connectivity tables (S must hold no storage; S.desc is set by the caller)
+// by depth, and the connectivity tables (S must hold no storage; the caller sets S.desc once this has succeeded)
 static int build_split(vrt_ctx* c, int s, int n_patches, const vrt_patch_desc* d) {
     VrtSpeciesState& S = c->S[s];
     const VrtSpecies sp = S.sp;
@@ -221,24 +222,15 @@ static int build_split(vrt_ctx* c, int s, int n_patches, const vrt_patch_desc* d
 }
 
 
-int vrt_set_hierarchy(vrt_ctx* c, int s, int n_patches, const vrt_patch_desc* d) {
-    if (!c) return VRT_ERR_ARG;
-    if (!check(c, c->grid_set && s >= 0 && s < c->n_species && c->S[s].configured, "vrt_set_hierarchy: set grid and species first")) return VRT_ERR_STATE;
-    if (!check(c, n_patches >= 1 && d, "vrt_set_hierarchy: bad arguments")) return VRT_ERR_ARG;
-    cudaSetDevice(c->device);
-    VRT_CUDA(c, cudaStreamSynchronize(c->stream));
-    drop_graphs(c);
-    VrtSpeciesState& S = c->S[s];
-    VrtSpecies sp = S.sp;
-    free_species(S);
-    S.sp = sp; S.configured = true;
+// Validation of a hierarchy and the path it would take, without touching any state (vrt_set_hierarchy and the first pass of
+// vrt_checkpoint_read, which must not modify the context before the whole file has been checked).
+int vrt_hierarchy_path(vrt_ctx* c, int n_patches, const vrt_patch_desc* d, int* path_out) {
     const int r = c->refinement_ratio;
     for (int p = 0; p < n_patches; p++) {
         const vrt_patch_desc& q = d[p];
         if (!check(c, q.depth >= 0 && q.depth <= c->max_depth && q.n_x >= r && q.n_p >= r && q.n_x % r == 0 && q.n_p % r == 0,
                    "vrt_set_hierarchy: bad patch descriptor")) return VRT_ERR_ARG;
     }
-    S.desc.assign(d, d + n_patches);
     // path selection: the fused streaming kernel serves single-level full-domain patches (optionally x-slabs)
     const vrt_patch_desc& q0 = d[0];
     const bool full = (n_patches == 1 && c->max_depth == 0 && q0.depth == 0 && q0.x_pos == 0 && q0.p_pos == 0 && q0.n_x == c->F.N &&
@@ -247,6 +239,53 @@ int vrt_set_hierarchy(vrt_ctx* c, int s, int n_patches, const vrt_patch_desc* d)
     if (path == VRT_PATH_AUTO) path = full ? VRT_PATH_FUSED : VRT_PATH_SPLIT;
     if (!check(c, path != VRT_PATH_FUSED || full, "vrt_set_hierarchy: the fused path needs one full-domain single-level patch")) return VRT_ERR_ARG;
     if (!check(c, c->n_ranks == 1 || path == VRT_PATH_FUSED, "vrt_set_hierarchy: x-slabs need the fused path")) return VRT_ERR_ARG;
+    *path_out = path;
+    return 0;
+}
+// doubles per slab plane of the fused layout for n_x local columns of n_p cells (vrt_set_hierarchy; vrt_checkpoint_read sizes its
+// records with it): even pitch, 3 ghost columns per side, slack for the last strip's bulk load
+long vrt_slab_plane_doubles(int n_x_local, int n_p) {
+    const long pitch = ((n_p + VRT_SLAB_GH + 4 + 1) / 2) * 2;
+    return (long)(n_x_local + 2 * 3) * pitch + 1024;
+}
+// a context whose hierarchies could not be (re)built holds none: every later call fails with VRT_ERR_STATE instead of touching
+// half-built storage
+void vrt_invalidate_hierarchies(vrt_ctx* c) {
+    drop_graphs(c);
+    for (auto& S : c->S) { VrtSpecies sp = S.sp; const bool conf = S.configured; free_species(S); S.sp = sp; S.configured = conf; }
+}
+
+static int set_hierarchy_impl(vrt_ctx* c, int s, int n_patches, const vrt_patch_desc* d);
+
+int vrt_set_hierarchy(vrt_ctx* c, int s, int n_patches, const vrt_patch_desc* d) {
+    if (!c) return VRT_ERR_ARG;
+    if (!check(c, c->grid_set && s >= 0 && s < c->n_species && c->S[s].configured, "vrt_set_hierarchy: set grid and species first")) return VRT_ERR_STATE;
+    if (!check(c, n_patches >= 1 && d, "vrt_set_hierarchy: bad arguments")) return VRT_ERR_ARG;
+    int rc;
+    try { rc = set_hierarchy_impl(c, s, n_patches, d); }
+    catch (const std::exception&) { c->err = "vrt_set_hierarchy: out of host memory"; rc = VRT_ERR_NOMEM; }
+    if (rc) {      // no half-built species: storage released, descriptor list empty (ready() then answers VRT_ERR_STATE)
+        VrtSpeciesState& S = c->S[s];
+        VrtSpecies sp = S.sp;
+        const std::string msg = c->err;
+        free_species(S);
+        S.sp = sp; S.configured = true;
+        c->err = msg;
+    }
+    return rc;
+}
+
+static int set_hierarchy_impl(vrt_ctx* c, int s, int n_patches, const vrt_patch_desc* d) {
+    cudaSetDevice(c->device);
+    VRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    drop_graphs(c);
+    VrtSpeciesState& S = c->S[s];
+    VrtSpecies sp = S.sp;
+    free_species(S);
+    S.sp = sp; S.configured = true;
+    int path;
+    if (int rc = vrt_hierarchy_path(c, n_patches, d, &path)) return rc;
+    const vrt_patch_desc& q0 = d[0];
     S.path = path;
     int rc;
     if (path == VRT_PATH_FUSED) {
@@ -257,7 +296,7 @@ int vrt_set_hierarchy(vrt_ctx* c, int s, int n_patches, const vrt_patch_desc* d)
         // column layout: VRT_SLAB_GH ghost doubles, n_p cells, >= 4 ghost doubles; even pitch keeps every strip start
         // (VRT_SLAB_GH + j0 - 3, j0 even) 16-byte aligned for the bulk-async (TMA) column loads
         L.gx = 3; L.pitch = ((q0.n_p + VRT_SLAB_GH + 4 + 1) / 2) * 2;
-        L.plane = (long)(L.n_x + 2 * L.gx) * L.pitch + 1024;   // slack: the last strip's bulk load may run past the last column
+        L.plane = vrt_slab_plane_doubles(L.n_x, q0.n_p);       // incl. slack: the last strip's bulk load may run past the last column
         if (!check(c, L.plane < (1L << 31), "vrt_set_hierarchy: slab plane exceeds 2^31 cells (split the domain over more GPUs)")) return VRT_ERR_ARG;
         L.dx = c->F.dx; L.dp = sp.dp_finest;
         // two pooled allocations (uniform plane stride): each is one 3-D tensor {p, column, plane} for the TMA descriptors
@@ -270,9 +309,13 @@ int vrt_set_hierarchy(vrt_ctx* c, int s, int n_patches, const vrt_patch_desc* d)
         if ((rc = dev_alloc(c, S.allocations, &L.chargeR, L.n_x))) return rc;
         if ((rc = dev_alloc(c, S.allocations, &L.currentR, L.n_x))) return rc;
         S.i_f0 = S.i_f1 = 0;
-        return vrt_fused_make_maps(c, s);
+        if ((rc = vrt_fused_make_maps(c, s))) return rc;
+        S.desc.assign(d, d + n_patches);       // only a fully built species carries descriptors
+        return 0;
     }
-    return build_split(c, s, n_patches, d);
+    if ((rc = build_split(c, s, n_patches, d))) return rc;
+    S.desc.assign(d, d + n_patches);
+    return 0;
 }
 
 // Mesh::promoteHierarchyToMesh(false) without the host round trip: the new hierarchy's storage is
@@ -286,6 +329,9 @@ int vrt_regrid(vrt_ctx* c, int s, int n_patches, const vrt_patch_desc* d) {
     VrtSpeciesState& S = c->S[s];
     if (!check(c, S.path == VRT_PATH_SPLIT && c->max_depth >= 1, "vrt_regrid: only hierarchies on the split path regrid")) return VRT_ERR_STATE;
     const int r = c->refinement_ratio;
+    // the coarse -> fine transfer fills a one-coarse-cell ring, i.e. r fine ghost cells, and the padded layout holds 2 (the
+    // reference's own code carries the same restriction, Rectangle.cpp:892-918)
+    if (!check(c, r == 2, "vrt_regrid: the regrid data movers support refinement ratio 2 only")) return VRT_ERR_ARG;
     for (int p = 0; p < n_patches; p++) {
         const vrt_patch_desc& q = d[p];
         if (!check(c, q.depth >= 0 && q.depth <= c->max_depth && q.n_x >= r && q.n_p >= r && q.n_x % r == 0 && q.n_p % r == 0,
@@ -294,19 +340,23 @@ int vrt_regrid(vrt_ctx* c, int s, int n_patches, const vrt_patch_desc* d) {
     cudaSetDevice(c->device);
     VRT_CUDA(c, cudaStreamSynchronize(c->stream));
     drop_graphs(c);
-    // park the old storage
+    // park the old storage; it comes back unchanged if the new hierarchy cannot be built or filled
     VrtSpeciesState old;
-    old.allocations.swap(S.allocations); old.patches.swap(S.patches); old.table.swap(S.table); old.table_index.swap(S.table_index);
-    old.table_order.swap(S.table_order); old.level_patches.swap(S.level_patches); old.desc.swap(S.desc);
-    old.d_patches = S.d_patches; S.d_patches = nullptr;
-    old.conn_pool = S.conn_pool; S.conn_pool = nullptr;
-    S.has_amr = false;
-    S.desc.assign(d, d + n_patches);
-    int rc = build_split(c, s, n_patches, d);
+    auto exchange = [&]() {
+        old.allocations.swap(S.allocations); old.patches.swap(S.patches); old.table.swap(S.table); old.table_index.swap(S.table_index);
+        old.table_order.swap(S.table_order); old.level_patches.swap(S.level_patches); old.desc.swap(S.desc);
+        std::swap(old.d_patches, S.d_patches); std::swap(old.conn_pool, S.conn_pool); std::swap(old.has_amr, S.has_amr);
+    };
+    exchange();
+    int rc;
+    try { rc = build_split(c, s, n_patches, d); }
+    catch (const std::exception&) { c->err = "vrt_regrid: out of host memory"; rc = VRT_ERR_NOMEM; }
     const long l0 = c->launches;
     if (!rc) rc = vrt_amr_transfer(c, old, S);
     if (getenv("VRT_TRACE")) fprintf(stderr, "vrt_regrid: species %d, %zu -> %d patches, %ld transfer kernels on the device\n", s, old.desc.size(), n_patches, c->launches - l0);
     if (!rc) { cudaError_t e = cudaStreamSynchronize(c->stream); if (e != cudaSuccess) { c->err = std::string("vrt_regrid: ") + cudaGetErrorString(e); rc = VRT_ERR_CUDA; } }
+    if (rc) exchange();                       // the half-built new hierarchy is now in `old` and is released below
+    else S.desc.assign(d, d + n_patches);
     for (double* p : old.allocations) cudaFree(p);
     if (old.d_patches) cudaFree(old.d_patches);
     if (old.conn_pool) cudaFree(old.conn_pool);

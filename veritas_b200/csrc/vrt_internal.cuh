@@ -176,6 +176,13 @@ struct vrt_ctx {
         }                                                                                        \
     } while (0)
 
+// ---- helpers of vrt_abi.cu used by other units (internal; C linkage only because they are defined inside its extern "C" block)
+extern "C" {
+int vrt_hierarchy_path(vrt_ctx* c, int n_patches, const vrt_patch_desc* d, int* path_out);
+long vrt_slab_plane_doubles(int n_x_local, int n_p);
+void vrt_invalidate_hierarchies(vrt_ctx* c);
+}
+
 // ---- launchers implemented in the kernel translation units -----------------------------------------
 // split path (vrt_split.cu, compiled with -fmad=false)
 int vrt_split_substep(vrt_ctx* c, int s, int depth, const double* d_dt, int step, int substep);
