@@ -2,10 +2,13 @@
 """Benchmark of the Veritas 1D1P Vlasov advance on B200 (metric of BASELINE.json):
 phase-space cell-updates/s per RK stage = cells (both species) x 6 stages x steps / time.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c3|c5] [--scaling strong|weak]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3|c4|c5] [--scaling strong|weak]
 
 N = 1 : config 3 of BASELINE.json (uniform 65536 x 4096, single level, two species) — the largest single-GPU config.
 N > 1 : config 5 (uniform 262144 x 4096 split in x over the GPUs, strong scaling); launched by torchrun, one rank per GPU.
+--workload c1 | c2 | c4 : BASELINE.json's CPU-runnable configurations (2048 x 256 single level; 2 levels with the refinement in the
+high-momentum tail; 3 levels with a regrid every 22 steps) driven through the C++ host classes (oracle/_ref/host_harness: the
+reference's own driver loop compiled against veritas_b200/host), with the reference timed on the SAME configuration beside it.
 One "step" = SolverManager::Advance(dt): 6 RK stages of moments + Poisson + fused Vlasov stage (x2 species) + Maxwell.
 Inputs (f, fields) are resident in HBM for `value`; `e2e` drives the same steps through the host-facing API with the
 per-step host round trips of the reference's driver loop (CalculateDt -> 8 B D2H, laser boundary values + dt -> H2D,
@@ -35,16 +38,29 @@ REF_SAMPLE = (2048, 4096)
 REF_SAMPLE_TEXT = ("sample of config 3: 2048 of its 65536 columns x 4096 p-cells, 2 species, single level (the reference's dense "
                    "N x N Poisson matrix and 360 B/cell storage do not fit configs 3/5)")
 DENSITY = 0.1   # "laser pulse in underdense plasma" (BASELINE.json configs[0]); one Settings number (veritas.cpp:47)
+# BASELINE.json configs 1, 2, 4 as harness arguments (nx np Lfinest + keys): the C++ host classes run them
+HOST_WORKLOADS = {
+    "c1": (["2048", "256", "1"], [], "c1: uniform 2048x256 x-p mesh, single level, 2 species"),
+    "c2": (["1024", "128", "2"], ["refine_mode=1", "tail_p0=2", "regrid_every=22"],
+           "c2: 1024x128 coarse mesh, 2 levels, refinement forced into the high-momentum tail, regrid every 22 steps, 2 species"),
+    "c4": (["512", "64", "3"], ["regrid_every=22"], "c4: 512x64 coarse mesh, 3 levels, regrid every 22 steps (veritas.cpp:146-151), 2 species"),
+}
 
 
 # version of k_fused_stage the committed ncu traffic capture (profiles/fused_traffic.json) must match to be quoted as `traffic`
-FUSED_KERNEL_VERSION = "v16"
+FUSED_KERNEL_VERSION = "v17"
 
 
 def stage_bytes(cells_species, s):
     """Algorithmic bytes of one fused-stage launch: reads f^n (8 B; at s = 0 the same array as
     f^(s)), f^(s) (8), 2 s stored fluxes; writes f^(s+1) (8) and, except at s = 5, the new flux pair (16)."""
     return cells_species * (8 + (8 if s > 0 else 0) + 16 * s + 8 + (16 if s < 5 else 0))
+
+
+def stage_bytes_moved(cells_species, s):
+    """Bytes the shipped kernel moves by design: the algorithmic bytes plus the stage-0 low-order flux pair (written at s = 0,
+    read at s >= 1: +16 B per cell) minus the history pair stage 5 skips (tableau weight b_1 = 0: -16 B per cell)."""
+    return stage_bytes(cells_species, s) + cells_species * (16 - (16 if s == 5 else 0))
 
 
 class ClockSampler:
@@ -91,12 +107,75 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+
+def run_harness(exe, wl, steps, warmup, threads=None):
+    """One timed run of the reference's driver loop (CalculateDt + Advance per step, regrids outside the timed region) in the
+    harness build `exe`; returns the ORACLE_TIMING fields."""
+    size, keys, _ = HOST_WORKLOADS[wl]
+    cores = threads or os.cpu_count() or 1
+    env = dict(os.environ, OMP_NUM_THREADS=str(cores), OPENBLAS_NUM_THREADS="1")
+    out = subprocess.run([exe, "/dev/null"] + size + [str(DENSITY), str(steps)] + keys + ["time_only=1", f"warmup={warmup}"],
+                         env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, check=True).stdout
+    line = [l for l in out.splitlines() if l.startswith("ORACLE_TIMING")][-1]
+    kv = dict(x.split("=") for x in line.split()[1:])
+    return {"value": float(kv["cell_updates_per_s_per_stage"]), "seconds": float(kv["advance_s"]), "steps": int(kv["steps"]),
+            "cells": int(kv["cells"]), "launches": int(kv.get("gpu_launches", 0)), "cores": cores}
+
+
+def host_workload_line(args, impl):
+    """BASELINE.json configs 1, 2, 4 through the reference's own class API: impl "ours" = oracle/_ref/host_harness (the case
+    file compiled against veritas_b200/host + libveritas_b200.so), impl "reference" = oracle/_ref/ref_harness (against the
+    unmodified reference, all host cores).  Both time CalculateDt + Advance of every step from t = 3T; f stays resident on the
+    device between steps exactly as it stays in Rectangle::f, so the per-step host traffic of the GPU build is the 8-byte CFL
+    bound down and dt + 12 laser values up: value and e2e are the same measurement."""
+    wl = args.workload
+    text = HOST_WORKLOADS[wl][2] + f", laser-plasma case n={DENSITY} N_c, t>=3T"
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    host = os.path.join(ROOT, "oracle", "_ref", "host_harness")
+    cb = None
+    if os.path.exists(ref) and not args.no_cpu_baseline:
+        ref_steps = args.steps if impl == "reference" else min(args.steps, 22)
+        r = run_harness(ref, wl, ref_steps, 1 if impl == "reference" else 0)
+        cb = {"value": r["value"], "unit": "cell-updates/s", "cores": r["cores"], "kind": "reference", "same_config": True,
+              "sample": f"{text}; {r['steps']} steps of CalculateDt + SolverManager::Advance, OMP_NUM_THREADS={r['cores']}"}
+    if impl == "reference":
+        if cb is None:
+            return {"impl": "reference", "unavailable": "oracle/_ref/ref_harness missing (run __graft_entry__.build() in the build container)"}
+        return {"impl": "reference", "metric": "phase-space cell-updates/s per RK stage", "value": cb["value"], "unit": "cell-updates/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / r["steps"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": text}, "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    if not os.path.exists(host):
+        raise SystemExit("bench.py: oracle/_ref/host_harness missing (run __graft_entry__.build())")
+    sampler = ClockSampler(0)
+    sampler.start()
+    g = run_harness(host, wl, args.steps, max(args.warmup, 3), threads=4)
+    clocks = sampler.stop()
+    return {"metric": "phase-space cell-updates/s per RK stage", "value": g["value"], "unit": "cell-updates/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * g["seconds"] / g["steps"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": text + f"; {g['cells']} patch cells at the end; small meshes: an L2 flush is not applied "
+                                          "(the whole hierarchy is L2-resident in the reference-sized case; stated, not hidden)",
+                       "parallelism": "single GPU", "api": "C++ host classes (SolverManager::CalculateDt / Advance / reGrid)", "cuda_graph": True},
+            "clocks": clocks,
+            "e2e": {"value": g["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 104, "d2h_bytes_per_step": 8,
+                    "what": "the same measurement: the host classes' driver loop, host wall clock around CalculateDt + Advance"},
+            "gpu_launches": g["launches"],
+            "roofline": None, "roofline_note": "launch-latency-bound hierarchy of small patches (split path); the roofline figures are quoted on config 3",
+            "cpu_baseline": cb}
+
+
 def reference_arm(args, rank):
     """The reference's own CPU implementation (oracle/_ref/ref_harness = unmodified reference sources) on the host
     cores.  It cannot run configs 3/5 (dense N x N Poisson matrix: 34 GB / 550 GB, EMSolver.cpp:30-31), so each step is
     a step of REF_SAMPLE — config 3's p grid on 2048 of its columns, the same case file.  At most 40 steps are run (the value
     is a rate)."""
     if rank != 0:
+        return
+    if args.workload in HOST_WORKLOADS:
+        line = host_workload_line(args, "reference")
+        print(json.dumps(line))
         return
     harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
     nx, np_ = REF_SAMPLE
@@ -124,6 +203,17 @@ def reference_arm(args, rank):
         "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+def measure_fp64_peak():
+    """fp64 issue peak (warp-wide thread-instructions per second) of this device: tools/fp64_peak run now, else the committed
+    round-1 measurement"""
+    exe = os.path.join(ROOT, "tools", "fp64_peak")
+    try:
+        out = subprocess.run([exe], stdout=subprocess.PIPE, text=True, check=True, timeout=60).stdout
+        return float(json.loads(out.strip().splitlines()[-1])["fp64_instr_per_s"]), "tools/fp64_peak (DFMA micro-benchmark) run in this session"
+    except Exception:
+        return float(json.load(open(os.path.join(ROOT, "profiles", "fp64_peak_r1.json")))["fp64_instr_per_s"]), "profiles/fp64_peak_r1.json (round 1)"
 
 
 def cpu_baseline(budget_steps=6):
@@ -160,7 +250,13 @@ def main():
         reference_arm(args, rank)
         return
     args.warmup = max(args.warmup, 3)
+    if args.workload in HOST_WORKLOADS:
+        if world > 1:
+            raise SystemExit("bench.py: the AMR workloads are single-GPU (whole patches are not sharded; SURVEY.md §8(e))")
+        print(json.dumps(host_workload_line(args, "ours")))
+        return
 
+    import hashlib
     import numpy as np
     import torch
     import veritas_b200 as vb
@@ -237,7 +333,7 @@ def main():
 
     # ---- end to end through the host-facing API ----------------------------------------------------------------------
     # per step: CalculateDt (device reduction + 8 B D2H), laser values + dt (13 doubles H2D as launch parameters),
-    # Advance, and the 1-D arrays fileOutput would write (charge x2, PHI, E_x, a^2, Ey, Ez, By, Bz) D2H.
+    # Advance, and the 1-D arrays fileOutput would write (charge x2, PHI, E_x, a^2, Ey, Ez, By, Bz) D2H on rank 0.
     d2h = 8 + 8 * (2 * nx + nx + nx + (nx + 1) + 4 * (nx + 4))
     h2d = 13 * 8
     # host buffers of the 1-D outputs: pinned, as the contract asks for the host side of the timed copies
@@ -249,10 +345,11 @@ def main():
     for _ in range(args.steps):
         dte = run.calculate_dt()
         run.advance(dte)
-        for k, buf in hb.items():
-            ctx.get_1d(k, buf)
-        for w, buf in hf.items():
-            ctx.download_field(w, 0, buf)
+        if rank == 0:        # the 1-D arrays are replicated on every rank; one process writes the output files
+            for k, buf in hb.items():
+                ctx.get_1d(k, buf)
+            for w, buf in hf.items():
+                ctx.download_field(w, 0, buf)
     barrier()
     e2e_s = time.perf_counter() - t0
     if dist is not None:
@@ -299,25 +396,51 @@ def main():
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": None, "kernel": "k_fused_stage<S> (76 B/cell/stage algorithmic, averaged over the 6 stages; the kernel moves 16 B/cell/stage more for the stored stage-0 low-order fluxes)",
+                "traffic": None, "kernel": "k_fused_stage<S> (76 B/cell/stage algorithmic, averaged over the 6 stages; the kernel moves 13.3 B/cell/stage more: +16 for the stored stage-0 low-order fluxes, -16 at stage 5 which skips the pair with zero tableau weight)",
                 "per_stage_GBps": per_stage, "peak_source": peak_src,
                 "stage_cell_updates_per_s": round(6 * cells_loc / (tot_ms * 1e-3), 1)}
     breakdown["fused_stage"] = round(2 * tot_ms, 3)     # both species
-    # DRAM traffic of one launch of the stage kernel from the committed ncu --set full capture (same workload only), next to
-    # the algorithmic bytes of that launch
+    # second roof (north_star: "the slower of fp64 peak and HBM bandwidth"): fp64-pipe instructions the kernel issues per cell
+    # (interior x-loop of the shipped SASS, tools/sass_count.py -> profiles/fused_sass_counts.json, times the recomputed strip /
+    # chunk halo) against the fp64 issue peak measured in this session (tools/fp64_peak, a DFMA micro-benchmark)
+    try:
+        sc = json.load(open(os.path.join(ROOT, "profiles", "fused_sass_counts.json")))
+        plan = ctx.fused_plan(0)
+        halo = (plan["W"] / (plan["W"] - 6.0)) * ((nx // n_gpus) / plan["chunks"] + 6.0) / ((nx // n_gpus) / plan["chunks"])
+        per_cell = [sc["stages"][f"S{i}"]["fp64_per_column"] * halo for i in range(6)]
+        fp64_peak, fp64_src = measure_fp64_peak()
+        stage_ms = [sum(ev[r][2 * i + s][0].elapsed_time(ev[r][2 * i + s][1]) for r in range(reps) for s in range(2)) / (2 * reps) for i in range(6)]
+        instr = sum(per_cell) * cells_loc
+        fp64 = {"instr_per_cell": round(sum(per_cell) / 6, 1), "halo_factor": round(halo, 4), "peak_instr_per_s": fp64_peak, "peak_source": fp64_src,
+                "achieved_instr_per_s": instr / (tot_ms * 1e-3), "frac": round(instr / (tot_ms * 1e-3) / fp64_peak, 4),
+                "per_stage_frac": [round(per_cell[i] * cells_loc / (stage_ms[i] * 1e-3) / fp64_peak, 3) for i in range(6)],
+                "sass_version": sc.get("kernel_version"),
+                "bound_cell_updates_per_s": fp64_peak / (sum(per_cell) / 6)}
+        roofline["fp64"] = fp64
+        hbm_bound = peak * 1e9 / 76.0
+        roofline["hbm_bound_cell_updates_per_s"] = hbm_bound
+        roofline["binding"] = "fp64" if fp64["bound_cell_updates_per_s"] < hbm_bound else "hbm"
+        roofline["frac_of_binding"] = round(roofline["stage_cell_updates_per_s"] / min(hbm_bound, fp64["bound_cell_updates_per_s"]), 4)
+    except Exception as e:      # the roof is context, never a reason to lose the line
+        roofline["fp64"] = {"unavailable": repr(e)}
+    # DRAM traffic of the stage kernel from the committed ncu --set full capture of the shipped kernel version (same workload
+    # only): `traffic` = one launch of stage 3 (the median stage), next to the algorithmic bytes and the bytes the kernel is
+    # designed to move; the other captured stages are listed beside it
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "fused_traffic.json")))
         if wl == "c3" and n_gpus == 1:
             if tr.get("kernel_version") == FUSED_KERNEL_VERSION:
-                roofline["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
-                roofline["traffic_unit"] = f"bytes per launch of stage {tr['stage']} (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
+                st = tr["stages"]
+                head = "3" if "3" in st else sorted(st)[0]
+                roofline["traffic"] = st[head]["dram_bytes_read"] + st[head]["dram_bytes_write"]
+                roofline["traffic_unit"] = f"bytes per launch of stage {head} (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
                 roofline["traffic_source"] = tr["source"]
-            else:   # no ncu --set full capture of this kernel version yet: say what the last one measured instead of passing it off
-                roofline["traffic_note"] = (f"not captured for {FUSED_KERNEL_VERSION}; {tr.get('kernel_version')}: "
-                                            f"{tr['dram_bytes_read'] + tr['dram_bytes_write']:.4g} B per launch of stage {tr['stage']} "
-                                            f"({tr['source']}); {FUSED_KERNEL_VERSION} moves 16 B per cell more (stored low-order fluxes)")
-            roofline["traffic_algorithmic"] = float(stage_bytes(cells_loc, tr["stage"]))
-            roofline["traffic_moved_expected"] = float(stage_bytes(cells_loc, tr["stage"]) + 16 * cells_loc)
+                roofline["traffic_algorithmic"] = float(stage_bytes(cells_loc, int(head)))
+                roofline["traffic_moved_by_design"] = float(stage_bytes_moved(cells_loc, int(head)))
+                roofline["traffic_per_stage"] = {k: {"dram": v["dram_bytes_read"] + v["dram_bytes_write"], "algorithmic": float(stage_bytes(cells_loc, int(k))),
+                                                     "by_design": float(stage_bytes_moved(cells_loc, int(k)))} for k, v in sorted(st.items())}
+            else:   # no ncu --set full capture of this kernel version yet: say so instead of passing an older one off
+                roofline["traffic_note"] = f"not captured for {FUSED_KERNEL_VERSION} (profiles/fused_traffic.json holds {tr.get('kernel_version')})"
     except Exception:
         pass
     run_steps = args.warmup + 2 * args.steps + reps
@@ -330,6 +453,13 @@ def main():
     a2max = float(np.max(ctx.get_1d(S.A_SQUARED)))
     if not fields_ok or not all(np.isfinite(drift)) or max(drift) > 1e-9:
         raise SystemExit(f"bench.py: state is not finite / particle number drifted ({drift}); the measurement is void")
+
+    # fingerprint of the state the run ends in (rho, J, PHI, E_y, a^2 on rank 0): runs of the same workload and step counts on
+    # 2, 4 and 8 GPUs must print the same hash — the x-slab decomposition is bitwise transparent
+    hsh = hashlib.sha256()
+    for arr in (ctx.get_1d(S.CHARGE), ctx.get_1d(S.J), ctx.get_1d(S.PHI), ctx.download_field(S.EY, 0), ctx.get_1d(S.A_SQUARED)):
+        hsh.update(np.ascontiguousarray(arr).tobytes())
+    state_hash = hsh.hexdigest()[:32]
 
     if rank == 0:
         cb = None if (args.no_cpu_baseline or n_gpus > 1) else cpu_baseline()     # the CPU baseline is timed at N = 1 only
@@ -347,7 +477,7 @@ def main():
             "roofline": roofline,
             "breakdown_ms_per_step": breakdown,
             "checks": {"finite": fields_ok, "particle_number_rel_drift": drift, "max_a_squared": a2max,
-                       "fields_phase_steps": fields_steps, "steps_run": run_steps},
+                       "fields_phase_steps": fields_steps, "steps_run": run_steps, "state_hash": state_hash},
             "cpu_baseline": cb,
         }
         print(json.dumps(out))

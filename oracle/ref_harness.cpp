@@ -22,6 +22,7 @@
 //         patch_moments=0 (1, reference build only: before every dump run EMFieldSolver::AssembleRhoAndJ on the dumped state and
 //         add each patch's Rectangle::chargeR / currentR, what Level::CollectRhoAndJ sums, Level.cpp:42-62; the dumped charge /
 //         J / charges are then the moments of that state, which the next Advance recomputes at its stage 0 anyway)
+//         warmup=0 (time_only runs: that many steps run before the `steps` timed ones and are left out of ORACLE_TIMING)
 //
 //        ref_harness cluster cases.txt out.txt nx np Lfinest
 //   runs the regrid clustering members of Mesh (Mesh.cpp:298-792) on the flag sets of cases.txt, one case per line:
@@ -366,7 +367,7 @@ int main(int argc, char** argv) {
     std::map<std::string, double> kv = {{"dump_every", 1}, {"stage_dumps", 0}, {"regrid_every", 0}, {"threads", 0},
                                         {"refine_mode", 0}, {"tail_p0", 2}, {"pre_steps", -1}, {"time_only", 0},
                                         {"internals", 0}, {"a0", 1}, {"np_ion", 0},
-                                        {"file_output", 0}, {"precision", 15}, {"energy", 0}, {"compact", 0}, {"patch_moments", 0}};
+                                        {"file_output", 0}, {"precision", 15}, {"energy", 0}, {"compact", 0}, {"patch_moments", 0}, {"warmup", 0}};
     for (int i = 7; i < argc; i++) {
         std::string a = argv[i]; size_t e = a.find('=');
         if (e == std::string::npos || !kv.count(a.substr(0, e))) { fprintf(stderr, "bad arg %s\n", argv[i]); return 2; }
@@ -427,6 +428,9 @@ int main(int argc, char** argv) {
         return c;
     };
     long cells = count_cells();
+    const int warmup = time_only ? (int)kv["warmup"] : 0;
+    long launches = 0;
+    steps += warmup;
     for (int n = 1; n <= steps; n++) {
         auto t0 = std::chrono::steady_clock::now();
         double dt_adaptive = std::min(SM.CalculateDt(settings.cfl), dt);
@@ -443,9 +447,14 @@ int main(int argc, char** argv) {
         } else {
             SM.Advance(dt_adaptive);
         }
-        if (time_only && (n == steps || (regrid_every > 0 && counter >= regrid_every - 1))) SM.CalculateDt(settings.cfl);
-        advance_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        cell_updates += 6.0 * (double)cells;
+        if (time_only && (n == steps || n == warmup || (regrid_every > 0 && counter >= regrid_every - 1))) SM.CalculateDt(settings.cfl);
+        if (n > warmup) {
+            advance_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            cell_updates += 6.0 * (double)cells;
+#ifdef VRT_HOST_BUILD
+            launches += vrt_last_step_launches(settings.Gpu());
+#endif
+        }
         if (regrid_every > 0) {
             if (counter >= regrid_every - 1) { SM.reGrid(t); counter = 0; cells = count_cells(); } else counter++;
         }
@@ -458,7 +467,7 @@ int main(int argc, char** argv) {
     }
     if (g_out) fclose(g_out);
     // machine-readable timing line (CPU baseline): cells, steps, seconds in Advance, threads
-    printf("ORACLE_TIMING cells=%ld steps=%d advance_s=%.6f threads=%d cell_updates_per_s_per_stage=%.6e\n", cells, steps,
-           advance_seconds, omp_get_max_threads(), steps > 0 ? cell_updates / advance_seconds : 0.0);
+    printf("ORACLE_TIMING cells=%ld steps=%d advance_s=%.6f threads=%d cell_updates_per_s_per_stage=%.6e gpu_launches=%ld\n", cells, steps - warmup,
+           advance_seconds, omp_get_max_threads(), steps > warmup ? cell_updates / advance_seconds : 0.0, launches);
     return 0;
 }

@@ -45,3 +45,14 @@ def test_reference_arm_under_torchrun_prints_once():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["scaling"] == "strong" and "sample of config 5" in d["config"]["workload"]
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/ref_harness not built (run __graft_entry__.build())")
+def test_reference_arm_on_an_amr_workload():
+    """--workload c4 (BASELINE.json configs[3], 3 levels): the reference arm runs that very configuration (same_config)"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c4", "--steps", "2", "--warmup", "1"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["value"] > 1e5 and "3 levels" in d["config"]["workload"]
+    assert d["cpu_baseline"]["same_config"] is True and d["cpu_baseline"]["kind"] == "reference"

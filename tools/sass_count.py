@@ -3,7 +3,7 @@
 
     python tools/sass_count.py [--obj veritas_b200/build/vrt_fused.cu.o] [--version v17] [--write]
 
-For every instance k_fused_stage<S, U, 128, LEAN> it finds the innermost-largest loop of the interior body (the x-loop, unrolled U
+For every instance k_fused_stage<S, U, 128> it finds the innermost-largest loop of the interior body (the x-loop, unrolled U
 times), and reports per thread and column: all instructions, fp64-pipe instructions (DADD DMUL DFMA DSETP), and the opcode mix.
 --write stores profiles/fused_sass_counts.json, which bench.py uses as the numerator of the fp64 roofline (roofline.fp64)."""
 import argparse
@@ -74,7 +74,7 @@ def main():
     args = ap.parse_args()
     res = {}
     for name, body in functions(args.obj):
-        m = re.search(r"k_fused_stageILi(\d)ELi(\d)ELi(\d+)ELb([01])E", name)
+        m = re.search(r"k_fused_stageILi(\d)ELi(\d)ELi(\d+)E(?:Lb([01])E)?", name)
         if not m or m.group(3) != "128":
             continue
         S, U, lean = int(m.group(1)), int(m.group(2)), m.group(4) == "1"
@@ -87,7 +87,7 @@ def main():
         print(f"{k}: {r['instr_per_column']:.1f} instr / column, fp64 {r['fp64_per_column']:.1f}, local-memory ops per iteration "
               f"{r['local_memory_ops_per_iteration']}, mix {dict(list(r['mix_per_iteration'].items())[:12])}")
     if args.write:
-        out = {"kernel_version": args.version, "what": "interior x-loop of k_fused_stage<S, 4, 128, LEAN>, per thread and column "
+        out = {"kernel_version": args.version, "what": "interior x-loop of k_fused_stage<S, 4, 128>, per thread and column "
                "(cuobjdump -sass of veritas_b200/build/vrt_fused.cu.o, sm_100a); one thread-column = one cell plus the recomputed strip / chunk halo",
                "stages": res}
         json.dump(out, open(os.path.join(ROOT, "profiles", "fused_sass_counts.json"), "w"), indent=1)
