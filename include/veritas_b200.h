@@ -142,7 +142,9 @@ long vrt_last_step_launches(const vrt_ctx* ctx);
 int vrt_fused_plan(vrt_ctx* ctx, int s, int out[6]);
 
 /* option 0: replay vrt_step through a captured CUDA graph (default 1) or launch kernel by kernel (0);
- * option 1: run the species' Vlasov stages of one RK stage on concurrent streams / graph branches (default 1) */
+ * option 1: run the species' Vlasov stages of one RK stage on concurrent streams / graph branches (default 1);
+ * option 2: run the 1-D Maxwell stage of an RK stage as a branch concurrent with that stage's Poisson solve and Vlasov kernels
+ *           (default 1; it depends on the moments only, and writes a^2 into a second buffer that is exchanged at the join) */
 int vrt_set_option(vrt_ctx* ctx, int option, int value);
 /* Rectangle::InitializeDistribution (Rectangle.cpp:616-665) for the shipped Maxwellian slab
  * (Settings::InitialDistribution, veritas.cpp:107-115), evaluated on the device: sub-cell midpoint quadrature

@@ -16,7 +16,7 @@ fi
 # ncu --set full: one launch each of stages 0, 3, 5 (species 0 and 1 alternate; the 4th step is profiled: 3 warm-up steps x 2
 # species x 3 matching stages = 18 launches skipped)
 if [ -z "$SKIP_NCU" ]; then
-timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:k_fused_stage<[035]' -s 18 -c 6 -o gpurun_out/prof_fused_$TAG -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --skip-fields-phase > gpurun_out/prof_bench_$TAG.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k 'regex:k_fused_stageILi[035]E' -s 18 -c 6 -o gpurun_out/prof_fused_$TAG -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --skip-fields-phase > gpurun_out/prof_bench_$TAG.log 2>&1
 echo "ncu fused rc=$?"; tail -1 gpurun_out/prof_bench_$TAG.log | cut -c1-160
 python tools/ncu_summary.py gpurun_out/prof_fused_$TAG.ncu-rep > $P/ncu_fused_${KV}_${TAG}_summary.txt
 python tools/ncu_source_summary.py gpurun_out/prof_fused_$TAG.ncu-rep 30 > $P/ncu_fused_${KV}_${TAG}_source.txt 2>/dev/null
@@ -28,6 +28,10 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --c
 python tools/launch_summary.py gpurun_out/launches_$TAG.csv "python bench.py --steps 2 --warmup 3 --no-cpu-baseline --skip-fields-phase under ncu --metrics gpu__time_duration.sum ($KV)" > $P/launches_${TAG}_${KV}_summary.txt 2>/dev/null
 head -8 $P/launches_${TAG}_${KV}_summary.txt
 fi
+# launch list of the 3-level AMR workload through the host classes (what the step is made of)
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 3000 -c 1600 --csv --log-file gpurun_out/launches_c4_$TAG.csv oracle/_ref/host_harness /dev/null 512 64 3 0.1 12 regrid_every=22 time_only=1 warmup=2 > gpurun_out/launches_c4_bench_$TAG.log 2>&1
+python tools/launch_summary.py gpurun_out/launches_c4_$TAG.csv "host_harness 512 64 3 (config 4) under ncu --metrics gpu__time_duration.sum, 1600 launches from launch 3000 on" > $P/launches_c4_${TAG}_summary.txt 2>/dev/null
+head -40 $P/launches_c4_${TAG}_summary.txt
 for wl in c1 c2 c4; do
   timeout 600 python bench.py --workload $wl --steps 100 --warmup 5 > $P/bench_${wl}_$TAG.json 2> gpurun_out/bench_${wl}_$TAG.err; echo "bench $wl rc=$?"; cut -c1-400 $P/bench_${wl}_$TAG.json
 done

@@ -104,6 +104,9 @@ int vrt_destroy(vrt_ctx* c) {
     for (double* p : c->field_allocs) cudaFree(p);
     if (c->d_params) cudaFree(c->d_params);
     if (c->d_comm) cudaFree(c->d_comm);
+    if (c->field_stream) cudaStreamDestroy(c->field_stream);
+    if (c->ev_ffork) cudaEventDestroy(c->ev_ffork);
+    if (c->ev_fjoin) cudaEventDestroy(c->ev_fjoin);
     for (cudaStream_t st : c->aux_stream) if (st) cudaStreamDestroy(st);
     for (cudaEvent_t ev : c->aux_join) if (ev) cudaEventDestroy(ev);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -132,6 +135,7 @@ int vrt_set_grid(vrt_ctx* c, int N, double dx, int pre, int post, int r, int max
     int rc;
     for (int v = 0; v < 6; v++) if ((rc = dev_alloc(c, c->field_allocs, &F.Y[v], 8L * F.M))) return rc;
     if ((rc = dev_alloc(c, c->field_allocs, &F.a_squared, N + 1))) return rc;
+    if ((rc = dev_alloc(c, c->field_allocs, &c->asq_alt, N + 1))) return rc;
     if ((rc = dev_alloc(c, c->field_allocs, &F.PHI, N))) return rc;
     F.epad = std::max(2, (int)std::lround(std::pow((double)r, max_depth)));
     if (!check(c, F.epad < N / 2, "vrt_set_grid: too many levels for this x size")) return VRT_ERR_ARG;
@@ -766,11 +770,32 @@ static int vlasov_stages_all(vrt_ctx* c, int i) {
 // the six stages of SolverManager::Advance as stream work (SolverManager.cpp:28-39)
 static int enqueue_step(vrt_ctx* c) {
     int r;
+    const bool fork = c->fork_fields;
+    if (fork && !c->field_stream) {
+        VRT_CUDA(c, cudaStreamCreateWithFlags(&c->field_stream, cudaStreamNonBlocking));
+        VRT_CUDA(c, cudaEventCreateWithFlags(&c->ev_ffork, cudaEventDisableTiming));
+        VRT_CUDA(c, cudaEventCreateWithFlags(&c->ev_fjoin, cudaEventDisableTiming));
+    }
     for (int i = 0; i < 6; i++) {
         if ((r = moments_impl(c))) return r;
+        if (fork) {
+            // RGKStep(i) reads J and the fields only (EMSolver.cpp:479-553): a side branch next to UpdatePotential and Mesh::Advance,
+            // which read the a^2 and E of the stage's start; joined before the next stage's moments read the new A
+            cudaStream_t main_stream = c->stream;
+            VRT_CUDA(c, cudaEventRecord(c->ev_ffork, main_stream));
+            VRT_CUDA(c, cudaStreamWaitEvent(c->field_stream, c->ev_ffork, 0));
+            c->stream = c->field_stream;
+            r = vrt_fields_rhs_update_faces(c, i, c->d_params, c->asq_alt);
+            c->stream = main_stream;
+            if (r) return r;
+            VRT_CUDA(c, cudaEventRecord(c->ev_fjoin, c->field_stream));
+        }
         if ((r = vrt_fields_poisson(c))) return r;
         if ((r = vlasov_stages_all(c, i))) return r;
-        if ((r = vrt_fields_rhs_update_faces(c, i, c->d_params))) return r;
+        if (fork) {
+            VRT_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_fjoin, 0));
+            std::swap(c->F.a_squared, c->asq_alt);         // six exchanges per step: every step starts on the same buffer
+        } else if ((r = vrt_fields_rhs_update_faces(c, i, c->d_params))) return r;
     }
     if (c->n_ranks > 1 && (r = vrt_comm_wait_halo(c, -1))) return r;      // a finished step has its halos in place
     return 0;
@@ -818,8 +843,28 @@ int vrt_step_fields(vrt_ctx* c, double dt, const double laser[12]) {
     cudaSetDevice(c->device);
     if (int r = set_params_async(c, dt, laser)) return r;
     const long l0 = c->launches;
-    for (int i = 0; i < 6; i++) if (int r = vrt_fields_rhs_update_faces(c, i, c->d_params)) return r;
-    c->last_step_launches = c->launches - l0;
+    // the 18 launches of the six field stages as one graph (the fields-only phase of a fine mesh is tens of thousands of steps,
+    // veritas.cpp:135-144, each a chain of latency-bound 1-D kernels); dt and the laser values are read from the parameter block
+    if (c->use_graph) {
+        if (!c->graph_fields) {
+            VRT_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            int r = 0;
+            for (int i = 0; i < 6 && !r; i++) r = vrt_fields_rhs_update_faces(c, i, c->d_params);
+            cudaGraph_t g = nullptr;
+            cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+            c->graph_fields_launches = c->launches - l0;
+            if (r) { if (g) cudaGraphDestroy(g); return r; }
+            if (e != cudaSuccess) { c->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e); return VRT_ERR_CUDA; }
+            e = cudaGraphInstantiate(&c->graph_fields, g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) { c->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e); return VRT_ERR_CUDA; }
+        }
+        VRT_CUDA(c, cudaGraphLaunch(c->graph_fields, c->stream));
+        c->last_step_launches = c->graph_fields_launches;
+    } else {
+        for (int i = 0; i < 6; i++) if (int r = vrt_fields_rhs_update_faces(c, i, c->d_params)) return r;
+        c->last_step_launches = c->launches - l0;
+    }
     for (int i = 0; i < 6; i++) c->time = vrt_update_time(c->time, i, dt);
     return 0;
 }
@@ -836,6 +881,7 @@ int vrt_set_option(vrt_ctx* c, int option, int value) {
     if (!c) return VRT_ERR_ARG;
     if (option == 0) { c->use_graph = value != 0; return 0; }
     if (option == 1) { c->fork_species = value != 0; drop_graphs(c); return 0; }
+    if (option == 2) { c->fork_fields = value != 0; drop_graphs(c); return 0; }
     return VRT_ERR_ARG;
 }
 

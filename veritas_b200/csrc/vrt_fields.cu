@@ -328,8 +328,12 @@ int vrt_fields_init_tables(vrt_ctx* c) {
     return 0;
 }
 
-int vrt_fields_rhs_update_faces(vrt_ctx* c, int step, const VrtStepParams* d_params) {
-    VrtFields& F = c->F;
+// asq_out: where InterpolateToFaces writes a^2 at the x-faces (nullptr: F.a_squared).  Inside vrt_step the field stage runs
+// concurrently with the Vlasov stage of the same RK stage, which still reads the previous a^2: it then writes the context's
+// second buffer and the two are exchanged afterwards (enqueue_step, vrt_abi.cu).
+int vrt_fields_rhs_update_faces(vrt_ctx* c, int step, const VrtStepParams* d_params, double* asq_out) {
+    VrtFields F = c->F;
+    if (asq_out) F.a_squared = asq_out;
     k_field_rhs<<<grid1(F.M), 256, 0, c->stream>>>(F, step, d_params);
     k_field_update<<<dim3(grid1(F.M), 6), 256, 0, c->stream>>>(F, step, d_params);
     k_field_faces<<<grid1(F.N), 256, 0, c->stream>>>(F);

@@ -154,7 +154,7 @@ struct vrt_ctx {
     VrtStepParams* d_params = nullptr; VrtStepParams* h_params = nullptr;
     cudaGraphExec_t graph_step3[3] = {nullptr, nullptr, nullptr};   // keyed by the plane-rotation state at step start
     cudaGraphExec_t graph_fields = nullptr;
-    long graph_launches[3] = {0, 0, 0};
+    long graph_launches[3] = {0, 0, 0}, graph_fields_launches = 0;
     std::pair<int, int> graph_end_state[3][8];
     bool use_graph = true;
     long launches = 0, last_step_launches = 0;
@@ -165,6 +165,13 @@ struct vrt_ctx {
     std::vector<cudaEvent_t> aux_join;
     cudaEvent_t ev_fork = nullptr;
     bool fork_species = true;
+    // the 1-D Maxwell stage of an RK stage depends on the moments only (J) and is independent of that stage's Poisson solve and
+    // Vlasov kernels: inside vrt_step it runs on field_stream between ev_ffork and ev_fjoin and writes a^2 at the faces into
+    // asq_alt while the Vlasov kernels still read F.a_squared; the two pointers are exchanged at the join (six times per step)
+    cudaStream_t field_stream = nullptr;
+    cudaEvent_t ev_ffork = nullptr, ev_fjoin = nullptr;
+    double* asq_alt = nullptr;
+    bool fork_fields = true;
 };
 
 #define VRT_CUDA(ctx, call)                                                                      \
@@ -198,7 +205,7 @@ int vrt_amr_level_boundary_fluxes(vrt_ctx* c, int s, int depth, int step);
 int vrt_amr_transfer(vrt_ctx* c, const VrtSpeciesState& old_state, VrtSpeciesState& new_state);
 int vrt_amr_error_flags(vrt_ctx* c, int s, int patch, const double weights[5], double criteria, unsigned char* flags_host);
 // 1-D solver (vrt_fields.cu, compiled with -fmad=false)
-int vrt_fields_rhs_update_faces(vrt_ctx* c, int step, const VrtStepParams* d_params);
+int vrt_fields_rhs_update_faces(vrt_ctx* c, int step, const VrtStepParams* d_params, double* asq_out = nullptr);
 int vrt_fields_poisson(vrt_ctx* c);
 int vrt_fields_cfl(vrt_ctx* c);
 int vrt_fields_assemble_begin(vrt_ctx* c);
