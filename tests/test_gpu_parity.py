@@ -170,6 +170,27 @@ def test_poisson_against_dense_lu_oracle():
         ctx.close()
 
 
+def test_poisson_single_cta_equals_tiled_passes(monkeypatch):
+    """Short x grids (N <= 4096) run UpdatePotential + the E table as one single-CTA launch; it must produce the bits of the
+    five multi-CTA passes (same per-tile arithmetic, same fixed-order sums of tile partials), ragged last tile included."""
+    rng = np.random.default_rng(3)
+    for N in (40, 1024, 2048, 3000, 4096):
+        out = {}
+        for small in ("1", "0"):
+            monkeypatch.setenv("VRT_POISSON_SMALL", small)
+            ctx = vb.Context(1)
+            ctx.set_grid(N, 1e-5 / N, 2, 2, 2, 0)
+            ctx.set_species(0, S.M_E, -S.Q_E, -1.0e-21, 1e-23)
+            rho = np.random.default_rng(N).standard_normal(N) * 1e3
+            ctx.set_1d(S.CHARGE, rho - rho.mean()); ctx.set_1d(S.NEUTRALIZATION, rng.standard_normal(N) * 0 + 1e-3)
+            ctx.set_scalar(S.EX0, 0.125)
+            ctx.call("vrt_set_hierarchy", 0, 1, (vb.PatchDesc * 1)(vb.PatchDesc(depth=0, x_pos=0, p_pos=0, n_x=N, n_p=8, up=1, down=1, left=1, right=1)))
+            ctx.poisson(); ctx.poisson()          # twice: the incremental Ex0 update (quirk Q4) goes through both paths
+            out[small] = (ctx.get_1d(S.PHI), ctx.get_1d(S.EFIELD), ctx.get_scalar(S.EX0))
+            ctx.close()
+        assert np.array_equal(out["1"][0], out["0"][0]) and np.array_equal(out["1"][1], out["0"][1]) and out["1"][2] == out["0"][2], N
+
+
 def test_cfl_bound_matches_oracle():
     from oracle.port import SingleLevelOracle
     d = load_golden("single_128x64_steps")

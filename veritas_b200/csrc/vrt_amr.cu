@@ -20,6 +20,7 @@
 // face of the limiter sync is written by at most two strips which compute the same value, (iii) levels are separate launches
 // in the reference's order.
 #include "vrt_internal.cuh"
+#include "vrt_launch.cuh"
 #include "vrt_device.cuh"
 #include <algorithm>
 #include <cmath>
@@ -292,7 +293,7 @@ __global__ void k_error_flags(const VrtPatchDev* all, int patch, ErrW W, double 
 
 // ---- K3: same-level ghost copy, side strips only (corners belong to k_corners / k_ghost_coarse) ---------------------
 // thread t: [0, 2 n_p) cells of the xm / xp sides, [2 n_p, 2 n_p + 2 n_x) cells of the pm / pp sides; both ghost layers
-__global__ void k_ghost_same(const VrtPatchDev* level, const VrtPatchDev* all, int val, int r) {
+__global__ void k_ghost_same(const VrtPatchDev* level, const VrtPatchDev* all, int val, int r) { vrt_pdl_sync();
     const VrtPatchDev& P = level[blockIdx.y];
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int nx = P.n_x, np = P.n_p;
@@ -316,7 +317,7 @@ __global__ void k_ghost_same(const VrtPatchDev* level, const VrtPatchDev* all, i
 }
 
 // ---- K5: restriction of covered cells (Rectangle.cpp:314-337) -------------------------------------------------------
-__global__ void k_restrict(const VrtPatchDev* level, const VrtPatchDev* all, int val, int r) {
+__global__ void k_restrict(const VrtPatchDev* level, const VrtPatchDev* all, int val, int r) { vrt_pdl_sync();
     const VrtPatchDev& P = level[blockIdx.y];
     const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= P.npad) return;
@@ -351,12 +352,12 @@ __device__ void corner_cell(const VrtPatchDev& P, const VrtPatchDev* all, int va
         f[NS(P, g2, i * r + j)] = same_level_value(all, nb, P.x_pos + g2, P.p_pos + i * r + j, val);
     }
 }
-__global__ void k_corners(const VrtPatchDev* level, const VrtPatchDev* all, int val, int r) {
+__global__ void k_corners(const VrtPatchDev* level, const VrtPatchDev* all, int val, int r) { vrt_pdl_sync();
     if (threadIdx.x < 8) corner_cell(level[blockIdx.y], all, val, r, threadIdx.x);
 }
 
 // ---- K4: coarse -> fine ghost interpolation, one thread per strip with a coarser neighbour, then the corners ----------
-__global__ void k_ghost_coarse(const VrtPatchDev* level, const VrtPatchDev* all, int val, int r) {
+__global__ void k_ghost_coarse(const VrtPatchDev* level, const VrtPatchDev* all, int val, int r) { vrt_pdl_sync();
     const VrtPatchDev& P = level[blockIdx.y];
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int sx = P.ns_x - 2, sp = P.ns_p;
@@ -436,7 +437,7 @@ __device__ double rgk_flux(const VrtPatchDev* all, int p, int i, int j, int kind
     return dp_inv * (fm * am + w3 * (fp1 - fm1) * (ap1 - am1));
 }
 // faces flagged is_interrior_level_boundary_{x,p}: flux := mean of the finer patch's face fluxes (Rectangle.cpp:1313-1394)
-__global__ void k_level_boundary_fluxes(const VrtPatchDev* level, const VrtPatchDev* all, int step, int r, Sp sp, VrtFields F) {
+__global__ void k_level_boundary_fluxes(const VrtPatchDev* level, const VrtPatchDev* all, int step, int r, Sp sp, VrtFields F) { vrt_pdl_sync();
     const VrtPatchDev& P = level[blockIdx.y];
     const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= P.npad) return;
@@ -458,7 +459,7 @@ __global__ void k_level_boundary_fluxes(const VrtPatchDev* level, const VrtPatch
 // pass 4: CalculateSameBoundaryC -> SetCFromSameLevel (Rectangle.cpp:1835-1877, 1795-1833)
 // pass 5: CalculateDifferentBoundaryC -> SetCFromDifferentLevel (1706-1763, 1625-1704)
 // pass 6: UpdateSameBoundaryC -> UpdateCFromSameLevel (1919-1960, 1879-1917)
-__global__ void k_boundary_c(const VrtPatchDev* level, const VrtPatchDev* all, int pass, int r) {
+__global__ void k_boundary_c(const VrtPatchDev* level, const VrtPatchDev* all, int pass, int r) { vrt_pdl_sync();
     const VrtPatchDev& Cl = level[blockIdx.y];       // the caller
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     const int sx = Cl.ns_x - 2, sp = Cl.ns_p;
@@ -586,18 +587,26 @@ int vrt_amr_upload_connectivity(vrt_ctx* c, int s, const vrt_conn& C) {
 static unsigned blocks(long n, int b = 128) { return (unsigned)((n + b - 1) / b); }
 
 // Level::PushData(updateType, val) (Level.cpp:88-126): 0 restriction, 1 same-level strips, 2 coarser-level strips + corners,
-// 3 corners, 4 / 5 / 6 the three limiter-sync passes
+// 3 corners, 4 / 5 / 6 the three limiter-sync passes.  l = -1: every level in one launch — valid for the passes that only touch
+// patches of one level (1, 4, 6): inside such a pass the levels do not interact, and on a small hierarchy every launch saved is
+// several microseconds of the step.
 int vrt_amr_level_pass(vrt_ctx* c, int s, int l, int type, int val) {
     VrtSpeciesState& S = c->S[s];
     const int nl = (int)S.level_patches.size(), r = c->refinement_ratio;
-    if (l < 0 || l >= nl || type < 0 || type > 6) { c->err = "level pass: bad level or update type"; return VRT_ERR_ARG; }
-    const std::vector<int>& lp = S.level_patches[l];
-    if (lp.empty()) return 0;
+    if (l < -1 || l >= nl || type < 0 || type > 6) { c->err = "level pass: bad level or update type"; return VRT_ERR_ARG; }
+    if (l == -1 && !(type == 1 || type == 4 || type == 6)) { c->err = "level pass: this pass couples levels and runs level by level"; return VRT_ERR_ARG; }
     const VrtPatchDev* all = S.d_patches;
-    const VrtPatchDev* level = all + lp[0];
-    const unsigned np = (unsigned)lp.size();
+    int first = 0, count = (int)S.table.size();
+    if (l >= 0) {
+        const std::vector<int>& lp = S.level_patches[l];
+        if (lp.empty()) return 0;
+        first = lp[0]; count = (int)lp.size();
+    }
+    if (count == 0) return 0;
+    const VrtPatchDev* level = all + first;
+    const unsigned np = (unsigned)count;
     long perim = 0, strips = 0, npad = 0;
-    for (int p : lp) {
+    for (int p = first; p < first + count; p++) {
         const VrtPatchDev& T = S.table[p];
         perim = std::max<long>(perim, 2L * T.n_x + 2L * T.n_p);
         strips = std::max<long>(strips, 2L * (T.ns_x - 2) + 2L * T.ns_p);
@@ -606,39 +615,41 @@ int vrt_amr_level_pass(vrt_ctx* c, int s, int l, int type, int val) {
     switch (type) {
         case 0:
             if (l == 0 || S.level_patches[l - 1].empty()) return 0;      // nothing is nested without a finer level
-            k_restrict<<<dim3(blocks(npad, 256), np), 256, 0, c->stream>>>(level, all, val, r); break;
-        case 1: k_ghost_same<<<dim3(blocks(perim), np), 128, 0, c->stream>>>(level, all, val, r); break;
-        case 2: k_ghost_coarse<<<dim3(blocks(strips + 8), np), 128, 0, c->stream>>>(level, all, val, r); break;
-        case 3: k_corners<<<dim3(1, np), 32, 0, c->stream>>>(level, all, val, r); break;
+            vrt_launch(k_restrict, dim3(dim3(blocks(npad, 256), np)), dim3(256), c->stream, level, all, val, r); break;
+        case 1: vrt_launch(k_ghost_same, dim3(dim3(blocks(perim), np)), dim3(128), c->stream, level, all, val, r); break;
+        case 2: vrt_launch(k_ghost_coarse, dim3(dim3(blocks(strips + 8), np)), dim3(128), c->stream, level, all, val, r); break;
+        case 3: vrt_launch(k_corners, dim3(dim3(1, np)), dim3(32), c->stream, level, all, val, r); break;
         default:
             if (!S.has_amr) return 0;     // every strip faces the BoundaryCondition object: zero-trip loops (quirk Q8)
-            k_boundary_c<<<dim3(blocks(strips), np), 128, 0, c->stream>>>(level, all, type, r); break;
+            vrt_launch(k_boundary_c, dim3(dim3(blocks(strips), np)), dim3(128), c->stream, level, all, type, r); break;
     }
     c->launches += 1;
     VRT_CUDA(c, cudaGetLastError());
     return 0;
 }
 
-// Mesh::PushData(val) (Mesh.cpp:91-106)
+// Mesh::PushData(val) (Mesh.cpp:91-106): finest level's same-level copy, then per coarser level restriction + same-level copy,
+// the coarsest level's corners, then the coarse -> fine ghosts from coarse to fine.  Reordered without changing a value: the
+// restrictions read fine-patch interiors only (not the ghost layers the same-level copies write) and each level's same-level copy
+// reads interiors of its own level only — so all restrictions go first, level by level (a level's restriction averages cells the
+// finer level's restriction wrote), and the same-level copies of all levels follow in ONE launch.
 int vrt_amr_push_data(vrt_ctx* c, int s, int val) {
     const int nl = (int)c->S[s].level_patches.size();
     int rc;
-    if ((rc = vrt_amr_level_pass(c, s, 0, 1, val))) return rc;
-    for (int l = 1; l < nl; l++) {
-        if ((rc = vrt_amr_level_pass(c, s, l, 0, val))) return rc;
-        if ((rc = vrt_amr_level_pass(c, s, l, 1, val))) return rc;
-    }
+    for (int l = 1; l < nl; l++) if ((rc = vrt_amr_level_pass(c, s, l, 0, val))) return rc;
+    if ((rc = vrt_amr_level_pass(c, s, -1, 1, val))) return rc;
     if ((rc = vrt_amr_level_pass(c, s, nl - 1, 3, val))) return rc;
     for (int l = nl - 1; l > 0; l--) if ((rc = vrt_amr_level_pass(c, s, l - 1, 2, val))) return rc;
     return 0;
 }
 
-// Mesh::PushBoundaryC (Mesh.cpp:904-917): passes 4, 5, 6 over all levels, finest first
+// Mesh::PushBoundaryC (Mesh.cpp:904-917): passes 4, 5, 6 over all levels, finest first.  Passes 4 and 6 pair patches of one
+// level only: one launch each for all levels; pass 5 writes the coarse face next to a fine strip and stays level by level.
 int vrt_amr_push_boundary_c(vrt_ctx* c, int s) {
     const int nl = (int)c->S[s].level_patches.size();
-    for (int pass = 4; pass <= 6; pass++)
-        for (int l = 0; l < nl; l++) if (int rc = vrt_amr_level_pass(c, s, l, pass, 1)) return rc;
-    return 0;
+    if (int rc = vrt_amr_level_pass(c, s, -1, 4, 1)) return rc;
+    for (int l = 0; l < nl; l++) if (int rc = vrt_amr_level_pass(c, s, l, 5, 1)) return rc;
+    return vrt_amr_level_pass(c, s, -1, 6, 1);
 }
 
 int vrt_amr_level_boundary_fluxes(vrt_ctx* c, int s, int depth, int step) {
@@ -646,7 +657,7 @@ int vrt_amr_level_boundary_fluxes(vrt_ctx* c, int s, int depth, int step) {
     if (depth == 0 || S.level_patches[depth].empty() || S.level_patches[depth - 1].empty()) return 0;
     long m = 0;
     for (int p : S.level_patches[depth]) m = std::max(m, S.table[p].npad);
-    k_level_boundary_fluxes<<<dim3(blocks(m, 128), (unsigned)S.level_patches[depth].size()), 128, 0, c->stream>>>(
+    vrt_launch(k_level_boundary_fluxes, dim3(dim3(blocks(m, 128), (unsigned)S.level_patches[depth].size())), dim3(128), c->stream, 
         S.d_patches + S.level_patches[depth][0], S.d_patches, step, c->refinement_ratio, make_sp(S.sp), c->F);
     c->launches += 1;
     VRT_CUDA(c, cudaGetLastError());
@@ -662,7 +673,7 @@ int vrt_amr_level_boundary_fluxes_all(vrt_ctx* c, int s, int step) {
     for (size_t d = 1; d < S.level_patches.size(); d++)
         for (int p : S.level_patches[d]) { if (first < 0) first = p; m = std::max(m, S.table[p].npad); }
     if (first < 0 || !S.has_amr) return 0;
-    k_level_boundary_fluxes<<<dim3(blocks(m, 128), (unsigned)(S.table.size() - first)), 128, 0, c->stream>>>(
+    vrt_launch(k_level_boundary_fluxes, dim3(dim3(blocks(m, 128), (unsigned)(S.table.size() - first))), dim3(128), c->stream, 
         S.d_patches + first, S.d_patches, step, c->refinement_ratio, make_sp(S.sp), c->F);
     c->launches += 1;
     VRT_CUDA(c, cudaGetLastError());

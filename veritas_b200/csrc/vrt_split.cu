@@ -4,6 +4,7 @@
 // patch-descriptor table (blockIdx.y = patch).  Compiled with -fmad=false: bit-compatible with the
 // reference's non-FMA build in everything except libm log and the p-reduction order of the moments.
 #include "vrt_internal.cuh"
+#include "vrt_launch.cuh"
 #include "vrt_device.cuh"
 #include <algorithm>
 
@@ -20,7 +21,7 @@ bool g_tabs_loaded[64] = {};     // __constant__ memory is per device: one flag 
     const int nx = P.n_x, np = P.n_p; (void)nx; (void)np; (void)i; (void)j;
 
 // sub-step 0, part 1: advection speeds and WENO face values (Rectangle.cpp:1276-1312)
-__global__ void k_speeds_faces(const VrtPatchDev* patches, Sp sp, VrtFields F) {
+__global__ void k_speeds_faces(const VrtPatchDev* patches, Sp sp, VrtFields F) { vrt_pdl_sync();
     PATCH_THREAD_SETUP
     const double q = sp.q, dx_inv = 1 / P.dx, dp_inv = 1 / P.dp, cc = VRT_CS * VRT_CS * sp.m;
     if (i >= -1 && i <= nx + 1 && j >= -1 && j <= np) {
@@ -44,7 +45,7 @@ __global__ void k_speeds_faces(const VrtPatchDev* patches, Sp sp, VrtFields F) {
 
 // sub-step 0, part 2: high/low-order fluxes at faces not flagged as interior level boundaries (Rectangle.cpp:1313-1394;
 // flagged faces are filled by k_level_boundary_fluxes of vrt_amr.cu).  FxL/FpL hold slot 0 only (quirk Q1).
-__global__ void k_fluxes(const VrtPatchDev* patches, int step) {
+__global__ void k_fluxes(const VrtPatchDev* patches, int step) { vrt_pdl_sync();
     PATCH_THREAD_SETUP
     const double w3 = 1 / 48.0, dx_inv = 1 / P.dx, dp_inv = 1 / P.dp;
     const unsigned char fl = P.flags[c];
@@ -64,7 +65,7 @@ __global__ void k_fluxes(const VrtPatchDev* patches, int step) {
     }
 }
 // sub-step 0, part 3: RK combination over the whole padded array (Rectangle.cpp:1396-1517)
-__global__ void k_rk_combine(const VrtPatchDev* patches, int step, const double* d_dt) {
+__global__ void k_rk_combine(const VrtPatchDev* patches, int step, const double* d_dt) { vrt_pdl_sync();
     PATCH_THREAD_SETUP
     const double timestep = *d_dt;
     double a[6], aSum = 0.0;
@@ -78,7 +79,7 @@ __global__ void k_rk_combine(const VrtPatchDev* patches, int step, const double*
 
 // flux application in gather form, same summation order as the reference's serial scatter
 // (Rectangle.cpp:1518-1534 / 1595-1612; quirks Q11, Q14).  mode 0: f2 = f0 + FLS;  mode 1: f1 = f2 + C*FDS.
-__global__ void k_apply(const VrtPatchDev* patches, int mode) {
+__global__ void k_apply(const VrtPatchDev* patches, int mode) { vrt_pdl_sync();
     PATCH_THREAD_SETUP
     if (i < 0 || i >= nx || j < 0 || j >= np) return;
     const int xm = P.left ? 1 : 0, xp = P.right ? nx : nx + 1, pp = P.up ? np : np + 1, pm = P.down ? 1 : 0;
@@ -102,7 +103,7 @@ __global__ void k_apply(const VrtPatchDev* patches, int mode) {
 }
 
 // sub-step 1: Zalesak ratios R+- on [-1,n_x]x[-1,n_p] (Rectangle.cpp:1536-1579)
-__global__ void k_limiter_r(const VrtPatchDev* patches) {
+__global__ void k_limiter_r(const VrtPatchDev* patches) { vrt_pdl_sync();
     PATCH_THREAD_SETUP
     if (i < -1 || i > nx || j < -1 || j > np) return;
     const long cxp = c + P.pitch, cxm = c - P.pitch;
@@ -119,7 +120,7 @@ __global__ void k_limiter_r(const VrtPatchDev* patches) {
     P.Rm[c] = Pm > 0.0 ? vmin(1.0, Qm / Pm) : 0.0;
 }
 // sub-step 1: limiter C, 1.0 everywhere then the interior loop i in [1,n_x), j in [0,n_p) (Rectangle.cpp:1581-1594, quirk Q13)
-__global__ void k_limiter_c(const VrtPatchDev* patches) {
+__global__ void k_limiter_c(const VrtPatchDev* patches) { vrt_pdl_sync();
     PATCH_THREAD_SETUP
     double cx = 1.0, cp = 1.0;
     if (i >= 1 && i < nx && j >= 0 && j < np) {
@@ -130,7 +131,7 @@ __global__ void k_limiter_c(const VrtPatchDev* patches) {
     P.Cx[c] = cx; P.Cp[c] = cp;
 }
 // sub-step 3: f0 := f1 over the padded array (Rectangle.cpp:1614-1622)
-__global__ void k_commit(const VrtPatchDev* patches) {
+__global__ void k_commit(const VrtPatchDev* patches) { vrt_pdl_sync();
     PATCH_THREAD_SETUP
     P.f0[c] = P.f1[c];
 }
@@ -166,7 +167,7 @@ __device__ __forceinline__ double cell_a_sq(const VrtFields& F, int i) {   // EM
     return (ay * ay) + (az * az);
 }
 // grid: (n_x*rtb, patches); block reduces over p
-__global__ void __launch_bounds__(128) k_moments(const VrtPatchDev* patches, Sp sp, VrtFields F) {
+__global__ void __launch_bounds__(128) k_moments(const VrtPatchDev* patches, Sp sp, VrtFields F) { vrt_pdl_sync();
     const VrtPatchDev& P = patches[blockIdx.y];
     const int rtb = P.rtb;
     if ((int)blockIdx.x >= P.n_x * rtb) return;
@@ -295,22 +296,22 @@ int vrt_split_substep(vrt_ctx* c, int s, int depth, const double* d_dt, int step
     const VrtPatchDev* tab = S.d_patches + first;
     Sp sp = make_sp(S.sp);
     if (substep == 0) {
-        k_speeds_faces<<<grid, 256, 0, c->stream>>>(tab, sp, c->F);
-        k_fluxes<<<grid, 256, 0, c->stream>>>(tab, step);
+        vrt_launch(k_speeds_faces, dim3(grid), dim3(256), c->stream, tab, sp, c->F);
+        vrt_launch(k_fluxes, dim3(grid), dim3(256), c->stream, tab, step);
         c->launches += 2;
         if (int r = vrt_amr_level_boundary_fluxes(c, s, depth, step)) return r;
-        k_rk_combine<<<grid, 256, 0, c->stream>>>(tab, step, d_dt);
-        k_apply<<<grid, 256, 0, c->stream>>>(tab, 0);
+        vrt_launch(k_rk_combine, dim3(grid), dim3(256), c->stream, tab, step, d_dt);
+        vrt_launch(k_apply, dim3(grid), dim3(256), c->stream, tab, 0);
         c->launches += 2;
     } else if (substep == 1) {
-        k_limiter_r<<<grid, 256, 0, c->stream>>>(tab);
-        k_limiter_c<<<grid, 256, 0, c->stream>>>(tab);
+        vrt_launch(k_limiter_r, dim3(grid), dim3(256), c->stream, tab);
+        vrt_launch(k_limiter_c, dim3(grid), dim3(256), c->stream, tab);
         c->launches += 2;
     } else if (substep == 2) {
-        k_apply<<<grid, 256, 0, c->stream>>>(tab, 1);
+        vrt_launch(k_apply, dim3(grid), dim3(256), c->stream, tab, 1);
         c->launches += 1;
     } else if (substep == 3) {
-        k_commit<<<grid, 256, 0, c->stream>>>(tab);
+        vrt_launch(k_commit, dim3(grid), dim3(256), c->stream, tab);
         c->launches += 1;
     } else {
         c->err = "vrt_vlasov_substep: substep must be 0..3";
@@ -335,22 +336,22 @@ int vrt_split_substep_all(vrt_ctx* c, int s, const double* d_dt, int step, int s
     const VrtPatchDev* tab = S.d_patches;
     Sp sp = make_sp(S.sp);
     if (substep == 0) {
-        k_speeds_faces<<<grid, 256, 0, c->stream>>>(tab, sp, c->F);
-        k_fluxes<<<grid, 256, 0, c->stream>>>(tab, step);
+        vrt_launch(k_speeds_faces, dim3(grid), dim3(256), c->stream, tab, sp, c->F);
+        vrt_launch(k_fluxes, dim3(grid), dim3(256), c->stream, tab, step);
         c->launches += 2;
         if (int r = vrt_amr_level_boundary_fluxes_all(c, s, step)) return r;
-        k_rk_combine<<<grid, 256, 0, c->stream>>>(tab, step, d_dt);
-        k_apply<<<grid, 256, 0, c->stream>>>(tab, 0);
+        vrt_launch(k_rk_combine, dim3(grid), dim3(256), c->stream, tab, step, d_dt);
+        vrt_launch(k_apply, dim3(grid), dim3(256), c->stream, tab, 0);
         c->launches += 2;
     } else if (substep == 1) {
-        k_limiter_r<<<grid, 256, 0, c->stream>>>(tab);
-        k_limiter_c<<<grid, 256, 0, c->stream>>>(tab);
+        vrt_launch(k_limiter_r, dim3(grid), dim3(256), c->stream, tab);
+        vrt_launch(k_limiter_c, dim3(grid), dim3(256), c->stream, tab);
         c->launches += 2;
     } else if (substep == 2) {
-        k_apply<<<grid, 256, 0, c->stream>>>(tab, 1);
+        vrt_launch(k_apply, dim3(grid), dim3(256), c->stream, tab, 1);
         c->launches += 1;
     } else {
-        k_commit<<<grid, 256, 0, c->stream>>>(tab);
+        vrt_launch(k_commit, dim3(grid), dim3(256), c->stream, tab);
         c->launches += 1;
     }
     VRT_CUDA(c, cudaGetLastError());
@@ -364,7 +365,7 @@ int vrt_split_substep_all(vrt_ctx* c, int s, const double* d_dt, int step, int s
 // order and adds it to the species charge and the total current — the additions and their order are those of the reference's
 // per-level loops (chargeL = sum over rectangles, then charges += chargeL).
 struct LevelRanges { int n_levels; int first[16]; int count[16]; };
-__global__ void k_collect_moments(const VrtPatchDev* all, LevelRanges R, double* charges, double* J, int N) {
+__global__ void k_collect_moments(const VrtPatchDev* all, LevelRanges R, double* charges, double* J, int N) { vrt_pdl_sync();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     double ch = charges[i], cu = J[i];
@@ -387,12 +388,12 @@ int vrt_split_moments(vrt_ctx* c, int s) {
     Sp sp = make_sp(S.sp);
     int mx = 0;
     for (const VrtPatchDev& T : S.table) mx = std::max(mx, T.n_x * T.rtb);
-    k_moments<<<dim3(mx, (unsigned)S.table.size()), 128, 0, c->stream>>>(S.d_patches, sp, c->F);
+    vrt_launch(k_moments, dim3(dim3(mx, (unsigned)S.table.size())), dim3(128), c->stream, S.d_patches, sp, c->F);
     LevelRanges R{};
     R.n_levels = (int)S.level_patches.size();
     if (R.n_levels > 16) { c->err = "vrt_moments: more than 16 levels"; return VRT_ERR_ARG; }
     for (int d = 0; d < R.n_levels; d++) { R.count[d] = (int)S.level_patches[d].size(); R.first[d] = R.count[d] ? S.level_patches[d][0] : 0; }
-    k_collect_moments<<<(c->F.N + 255) / 256, 256, 0, c->stream>>>(S.d_patches, R, S.d_charges, c->F.J, c->F.N);
+    vrt_launch(k_collect_moments, dim3((c->F.N + 255) / 256), dim3(256), c->stream, S.d_patches, R, S.d_charges, c->F.J, c->F.N);
     c->launches += 2;
     VRT_CUDA(c, cudaGetLastError());
     return 0;
