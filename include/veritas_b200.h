@@ -161,6 +161,10 @@ int vrt_patch_energy(vrt_ctx* ctx, int s, int patch, double* energy_host);
 /* Binary image of the context at a step boundary: hierarchy and f of every species, the 1-D field arrays, PHI, Ex0, the
  * neutralisation charge and the time.  vrt_checkpoint_read needs a context with the same vrt_set_grid (and vrt_set_slab /
  * vrt_set_path) calls; it recreates the hierarchies itself.  A restarted run continues bit for bit.  One file per rank. */
+/* The hierarchy species s holds — the descriptors of the last vrt_set_hierarchy / vrt_regrid / vrt_checkpoint_read, in the caller's
+ * order: returns the patch count (negative: error) and fills at most `capacity` entries of `out` (NULL with capacity 0 to query the
+ * count).  Lets a host layer rebuild its Level / Rectangle objects after vrt_checkpoint_read (SolverManager::Restart). */
+int vrt_get_hierarchy(vrt_ctx* ctx, int s, int capacity, vrt_patch_desc* out);
 int vrt_checkpoint_write(vrt_ctx* ctx, const char* path);
 int vrt_checkpoint_read(vrt_ctx* ctx, const char* path);
 

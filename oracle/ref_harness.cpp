@@ -23,6 +23,9 @@
 //         add each patch's Rectangle::chargeR / currentR, what Level::CollectRhoAndJ sums, Level.cpp:42-62; the dumped charge /
 //         J / charges are then the moments of that state, which the next Advance recomputes at its stage 0 anyway)
 //         warmup=0 (time_only runs: that many steps run before the `steps` timed ones and are left out of ORACLE_TIMING)
+//         ckpt_write=K (host build only: SolverManager::Checkpoint into <out>.ckpt after step K, with the driver loop's own
+//         counters in <out>.ckpt.meta)  ckpt_restart=1 (host build only: skip the fields-only phase and the steps up to the
+//         checkpoint, SolverManager::Restart from <out>.ckpt, continue with the remaining steps); $VRT_HARNESS_CKPT overrides the path
 //
 //        ref_harness cluster cases.txt out.txt nx np Lfinest
 //   runs the regrid clustering members of Mesh (Mesh.cpp:298-792) on the flag sets of cases.txt, one case per line:
@@ -367,7 +370,7 @@ int main(int argc, char** argv) {
     std::map<std::string, double> kv = {{"dump_every", 1}, {"stage_dumps", 0}, {"regrid_every", 0}, {"threads", 0},
                                         {"refine_mode", 0}, {"tail_p0", 2}, {"pre_steps", -1}, {"time_only", 0},
                                         {"internals", 0}, {"a0", 1}, {"np_ion", 0},
-                                        {"file_output", 0}, {"precision", 15}, {"energy", 0}, {"compact", 0}, {"patch_moments", 0}, {"warmup", 0}};
+                                        {"file_output", 0}, {"precision", 15}, {"energy", 0}, {"compact", 0}, {"patch_moments", 0}, {"warmup", 0}, {"ckpt_write", 0}, {"ckpt_restart", 0}};
     for (int i = 7; i < argc; i++) {
         std::string a = argv[i]; size_t e = a.find('=');
         if (e == std::string::npos || !kv.count(a.substr(0, e))) { fprintf(stderr, "bad arg %s\n", argv[i]); return 2; }
@@ -399,8 +402,23 @@ int main(int argc, char** argv) {
     double dt = T / 400, t = dt;
     int pre_steps = (int)kv["pre_steps"];
     int n_pre = 0;
+    const int ckpt_write = (int)kv["ckpt_write"];
+    const bool ckpt_restart = kv["ckpt_restart"] != 0;
+    const std::string ckpt_path = getenv("VRT_HARNESS_CKPT") ? std::string(getenv("VRT_HARNESS_CKPT")) : std::string(out) + ".ckpt";
+    int first_step = 1, counter = 0;
+#ifndef VRT_HOST_BUILD
+    if (ckpt_write || ckpt_restart) { fprintf(stderr, "ckpt_write / ckpt_restart need the veritas_b200 host build\n"); return 2; }
+#else
+    if (ckpt_restart) {
+        SM.Restart(ckpt_path);
+        FILE* m = fopen((ckpt_path + ".meta").c_str(), "r");
+        if (!m || fscanf(m, "%d %d %d %la", &first_step, &counter, &n_pre, &t) != 4) { fprintf(stderr, "cannot read %s.meta\n", ckpt_path.c_str()); return 1; }
+        fclose(m);
+        first_step += 1;
+    }
+#endif
     // fields-only phase, exactly as the shipped main(): while t <= 3T (veritas.cpp:135-144)
-    while (pre_steps < 0 ? !(t > 3 * T) : n_pre < pre_steps) {
+    while (!ckpt_restart && (pre_steps < 0 ? !(t > 3 * T) : n_pre < pre_steps)) {
         SM.AdvanceFields(dt);
         t += dt; n_pre++;
     }
@@ -414,9 +432,9 @@ int main(int argc, char** argv) {
         }
         double em[2] = {settings.tempEM[0], settings.tempEM[1]};
         put("tempEM", em, {2});
-        dump_state(SM, settings, "step0", internals);
+        if (!ckpt_restart) dump_state(SM, settings, "step0", internals);
     }
-    int counter = 0, regrid_every = (int)kv["regrid_every"], dump_every = (int)kv["dump_every"];
+    int regrid_every = (int)kv["regrid_every"], dump_every = (int)kv["dump_every"];
     bool stage_dumps = kv["stage_dumps"] != 0;
     // timing (CPU baseline / drop-in comparison): CalculateDt + Advance of every step, as in the reference's main loop
     // (veritas.cpp:137-144).  The GPU build's Advance only enqueues work; the next CalculateDt reads the CFL bound back and
@@ -431,7 +449,7 @@ int main(int argc, char** argv) {
     const int warmup = time_only ? (int)kv["warmup"] : 0;
     long launches = 0;
     steps += warmup;
-    for (int n = 1; n <= steps; n++) {
+    for (int n = first_step; n <= steps; n++) {
         auto t0 = std::chrono::steady_clock::now();
         double dt_adaptive = std::min(SM.CalculateDt(settings.cfl), dt);
         if (stage_dumps && !time_only) {
@@ -464,6 +482,14 @@ int main(int argc, char** argv) {
             put1("step" + std::to_string(n) + "/dt", dt_adaptive);
             dump_state(SM, settings, "step" + std::to_string(n), internals);
         }
+#ifdef VRT_HOST_BUILD
+        if (ckpt_write > 0 && n == ckpt_write) {
+            SM.Checkpoint(ckpt_path);
+            FILE* m = fopen((ckpt_path + ".meta").c_str(), "w");
+            fprintf(m, "%d %d %d %a\n", n, counter, n_pre, t);
+            fclose(m);
+        }
+#endif
     }
     if (g_out) fclose(g_out);
     // machine-readable timing line (CPU baseline): cells, steps, seconds in Advance, threads

@@ -39,6 +39,7 @@ SIGNATURES = {
     "vrt_set_hierarchy": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(PatchDesc)]),
     "vrt_regrid": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(PatchDesc)]),
     "vrt_patch_energy": (C.c_int, [C.c_void_p, C.c_int, C.c_int, dbl_p]),
+    "vrt_get_hierarchy": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(PatchDesc)]),
     "vrt_checkpoint_write": (C.c_int, [C.c_void_p, C.c_char_p]),
     "vrt_checkpoint_read": (C.c_int, [C.c_void_p, C.c_char_p]),
     "vrt_error_flags": (C.c_int, [C.c_void_p, C.c_int, C.c_int, dbl_p, C.c_double, C.POINTER(C.c_ubyte)]),

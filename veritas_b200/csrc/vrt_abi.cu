@@ -871,6 +871,13 @@ int vrt_step_fields(vrt_ctx* c, double dt, const double laser[12]) {
 
 long vrt_last_step_launches(const vrt_ctx* c) { return c ? c->last_step_launches : 0; }
 
+int vrt_get_hierarchy(vrt_ctx* c, int s, int capacity, vrt_patch_desc* out) {
+    if (int r = ready_species(c, s)) return r;
+    const std::vector<vrt_patch_desc>& d = c->S[s].desc;
+    if (out) for (int k = 0; k < capacity && k < (int)d.size(); k++) out[k] = d[k];
+    return (int)d.size();
+}
+
 int vrt_fused_plan(vrt_ctx* c, int s, int out[6]) {
     if (int r = ready_species(c, s)) return r;
     if (!check(c, out && c->S[s].path == VRT_PATH_FUSED, "vrt_fused_plan: species is not on the fused path")) return VRT_ERR_STATE;

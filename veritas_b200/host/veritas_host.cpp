@@ -681,6 +681,30 @@ void Mesh::promoteHierarchyToMesh(bool init) {
     device_current_ = true;
 }
 
+// After vrt_checkpoint_read the device holds the checkpoint's hierarchy: rebuild the Level / Rectangle objects (same order as
+// promoteHierarchyToMesh numbers them: levels by depth, rectangles in stored order) and the level boxes the next regrid starts
+// from.  Rectangle::f of the new objects is a stale mirror until the next SyncHost().
+void Mesh::AdoptDeviceHierarchy() {
+    vrt_ctx* g = settings.Gpu();
+    const int n = vrt_get_hierarchy(g, particleType, 0, nullptr);
+    if (n < 1) settings.Check(n < 0 ? n : -1, "vrt_get_hierarchy");
+    std::vector<vrt_patch_desc> d(n);
+    vrt_get_hierarchy(g, particleType, n, d.data());
+    levels.clear();
+    for (int depth = 0; depth <= settings.maxDepth; depth++) levels.push_back(std::make_unique<Level>(particleType, depth, settings));
+    int id = 0, min_depth = settings.maxDepth;
+    for (const vrt_patch_desc& q : d) {
+        auto r = std::make_shared<Rectangle>(q.n_x, q.n_p, q.x_pos, q.p_pos, q.depth, settings, bc, q.up != 0, q.down != 0, q.left != 0, q.right != 0, particleType);
+        r->patch_id = id++;
+        levels.at(q.depth)->rectangles.push_back(r);
+        min_depth = std::min(min_depth, q.depth);
+    }
+    hierarchy.assign(settings.maxDepth - min_depth + 1, level());
+    for (const vrt_patch_desc& q : d)
+        hierarchy.at(settings.maxDepth - q.depth).push_back(std::make_pair(std::make_pair(q.x_pos, q.p_pos), std::make_pair(q.x_pos + q.n_x, q.p_pos + q.n_p)));
+    device_current_ = true;
+}
+
 // Mesh::outputRectangleData (Mesh.cpp:877-902): one text file per level, "r x_pos p_pos n_x n_p" then "i j f" per cell (state 0)
 void Mesh::outputRectangleData(double tidx) {
     SyncHost();
@@ -932,6 +956,18 @@ void SolverManager::fileOutput(double t) {                 // SolverManager.cpp:
     if (o.BFieldTransverse) EMSolver->DumpBFieldTransverse();
     if (o.AFieldSquared) EMSolver->DumpAsqField();
     if (o.time) EMSolver->DumpTime(t);
+}
+void SolverManager::Checkpoint(const std::string& path) {
+    settings.Check(vrt_set_scalar(settings.Gpu(), VRT_TIME, settings.time), "vrt_set_scalar");
+    settings.Check(vrt_checkpoint_write(settings.Gpu(), path.c_str()), "vrt_checkpoint_write");
+}
+void SolverManager::Restart(const std::string& path) {
+    settings.Check(vrt_checkpoint_read(settings.Gpu(), path.c_str()), "vrt_checkpoint_read");
+    double t = 0.0;
+    settings.Check(vrt_get_scalar(settings.Gpu(), VRT_TIME, &t), "vrt_get_scalar");
+    settings.time = t;
+    for (auto& mesh : meshes) mesh->AdoptDeviceHierarchy();
+    EMSolver->Invalidate();
 }
 void SolverManager::SyncHost() {
     for (auto& mesh : meshes) mesh->SyncHost();

@@ -228,6 +228,7 @@ public:
     // veritas_b200 additions
     void SyncHost();                   // device -> Rectangle::f (states 0 and 1, ghosts included)
     void MarkDeviceCurrent() { device_current_ = true; }
+    void AdoptDeviceHierarchy();       // Level / Rectangle objects and `hierarchy` from the descriptors the device holds (restart)
     const std::vector<level>& Hierarchy() const { return hierarchy; }
 };
 
@@ -289,6 +290,10 @@ public:
     double CalculateDt(double cfl);
     // veritas_b200 addition: refresh every host mirror (Rectangle::f, EMFieldSolver arrays) from the device
     void SyncHost();
+    // veritas_b200 additions (the reference has no restart): binary checkpoint of the whole solver state at a
+    // step boundary, and its restoration into a SolverManager constructed from the same Settings — the run continues bit for bit
+    void Checkpoint(const std::string& path);
+    void Restart(const std::string& path);
 };
 
 inline double Rectangle::Momentum(double i) const { return settings_->pmin[particleType] + dp * (i + p_pos); }
