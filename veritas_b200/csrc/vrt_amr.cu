@@ -178,55 +178,72 @@ __device__ __forceinline__ double same_level_value(const VrtPatchDev* all, int n
     const VrtPatchDev& Q = all[nb];
     return fstate(Q, val)[NS(Q, i - Q.x_pos, j - Q.p_pos)];
 }
-// Rectangle::GetInterpolantsREF (Rectangle.cpp:121-137) with the coefficients of Rectangle.cpp:94-101 evaluated in place
-__device__ void interpolants_ref(int r, double f1, double f2, double f3, double f4, double f5, double* out) {
+// Rectangle::GetInterpolantsREF (Rectangle.cpp:121-137) with the coefficients of Rectangle.cpp:94-101 evaluated in place.
+// R = refinement ratio at compile time (0: run-time r).  With R = 2 — the only ratio the regrid path supports and the one every
+// BASELINE config uses — the sub-cell loops unroll, the sub-cell coefficients fold to constants (the same IEEE operations, this unit is
+// compiled with -fmad=false) and the small work arrays live in registers instead of local memory: the coarse -> fine ghost kernel,
+// one thread per strip and therefore pure latency, was 56 % of the kernel time of a 3-level step before (profiles/launches_c4_r2e.txt).
+constexpr int RMAX = 4;   // largest refinement ratio the interpolation buffers are sized for
+template <int R>
+__device__ __forceinline__ void interpolants_ref_t(int r, double f1, double f2, double f3, double f4, double f5, double* out) {
+    const int rr = R ? R : r;
     f5 -= f3; f4 -= f3; f2 -= f3; f1 -= f3;
     double a1 = c_IMr[0] * f1 + c_IMr[1] * f2 + c_IMr[2] * f4 + c_IMr[3] * f5;
     double a2 = c_IMr[4] * f1 + c_IMr[5] * f2 + c_IMr[6] * f4 + c_IMr[7] * f5;
     double a3 = c_IMr[8] * f1 + c_IMr[9] * f2 + c_IMr[10] * f4 + c_IMr[11] * f5;
-    for (int i = 0; i < r; i++) {
-        double tl = -0.5 + i / (double)r, tr = -0.5 + (i + 1.0) / (double)r;
+#pragma unroll
+    for (int i = 0; i < (R ? R : RMAX); i++) {
+        if (i >= rr) break;
+        double tl = -0.5 + i / (double)rr, tr = -0.5 + (i + 1.0) / (double)rr;
         double c0 = (tl + tr) * 0.5;
         double c1 = (tl * tl + tl * tr + tr * tr) / 3.0 - (1.0 / 12);
         double c2 = (tl * tl * tl + tl * tl * tr + tl * tr * tr + tr * tr * tr) * 0.25;
         out[i] = c0 * a1 + c1 * a2 + c2 * a3 + f3;
     }
 }
-constexpr int RMAX = 4;   // largest refinement ratio the interpolation buffers are sized for
-// Rectangle::GetWenoValueFromCoarseLevel (Rectangle.cpp:343-415) on coarse patch Q; (i,j) are fine-level global cell
-// coordinates; out receives the two sub-cell layers nearest the fine patch (2r values) for d = 0..3
-__device__ void coarse_level_values(const VrtPatchDev& Q, int r, int i, int j, int d, int val, double* out) {
+// the r x r sub-cells of the coarse cell of patch Q under fine cell (i, j) (fine-level global coordinates), with the mean-preserving
+// correction: ip[k * r + l] = sub-cell (x k, p l) — Rectangle::GetWenoValueFromCoarseLevel (Rectangle.cpp:343-415)
+template <int R>
+__device__ __forceinline__ void coarse_block_t(const VrtPatchDev& Q, int r, int i, int j, int val, double* ip) {
+    const int rr = R ? R : r;
     const double* f = fstate(Q, val);
-    const int ic = i / r - Q.x_pos, jc = j / r - Q.p_pos;
-    double temps[5][RMAX], ip[RMAX * RMAX], part[RMAX], sum = 0.0;
-    for (int k = -2; k < 3; k++)
-        interpolants_ref(r, f[NS(Q, ic - 2, jc + k)], f[NS(Q, ic - 1, jc + k)], f[NS(Q, ic, jc + k)], f[NS(Q, ic + 1, jc + k)], f[NS(Q, ic + 2, jc + k)], temps[k + 2]);
-    for (int k = 0; k < r; k++) {
-        interpolants_ref(r, temps[0][k], temps[1][k], temps[2][k], temps[3][k], temps[4][k], part);
-        for (int l = 0; l < r; l++) { ip[k * r + l] = part[l]; sum += part[l]; }
-    }
-    const double correction = f[NS(Q, ic, jc)] - 1.0 / (double)(r * r) * sum;
-    for (int k = 0; k < r * r; k++) ip[k] += correction;
-    if (d == 0) for (int k = 0; k < r; k++) { out[2 * k] = ip[r * k + r - 1]; out[2 * k + 1] = ip[r * k + r - 2]; }
-    else if (d == 1) for (int k = 0; k < r; k++) { out[2 * k] = ip[k]; out[2 * k + 1] = ip[r + k]; }
-    else if (d == 2) for (int k = 0; k < r; k++) { out[2 * k] = ip[r * k]; out[2 * k + 1] = ip[r * k + 1]; }
-    else for (int k = 0; k < r; k++) { out[2 * k] = ip[r * (r - 1) + k]; out[2 * k + 1] = ip[r * (r - 2) + k]; }
-}
-
-// the same interpolation, all r x r sub-cells of the coarse cell under fine cell (i, j): ip[k * r + l] = sub-cell (x k, p l)
-// (GetWenoValueFromCoarseLevel with d = -1, used by the regrid data transfer)
-__device__ void coarse_level_block(const VrtPatchDev& Q, int r, int i, int j, int val, double* ip) {
-    const double* f = fstate(Q, val);
-    const int ic = i / r - Q.x_pos, jc = j / r - Q.p_pos;
+    const int ic = i / rr - Q.x_pos, jc = j / rr - Q.p_pos;
     double temps[5][RMAX], part[RMAX], sum = 0.0;
+#pragma unroll
     for (int k = -2; k < 3; k++)
-        interpolants_ref(r, f[NS(Q, ic - 2, jc + k)], f[NS(Q, ic - 1, jc + k)], f[NS(Q, ic, jc + k)], f[NS(Q, ic + 1, jc + k)], f[NS(Q, ic + 2, jc + k)], temps[k + 2]);
-    for (int k = 0; k < r; k++) {
-        interpolants_ref(r, temps[0][k], temps[1][k], temps[2][k], temps[3][k], temps[4][k], part);
-        for (int l = 0; l < r; l++) { ip[k * r + l] = part[l]; sum += part[l]; }
+        interpolants_ref_t<R>(r, f[NS(Q, ic - 2, jc + k)], f[NS(Q, ic - 1, jc + k)], f[NS(Q, ic, jc + k)], f[NS(Q, ic + 1, jc + k)], f[NS(Q, ic + 2, jc + k)], temps[k + 2]);
+#pragma unroll
+    for (int k = 0; k < (R ? R : RMAX); k++) {
+        if (k >= rr) break;
+        interpolants_ref_t<R>(r, temps[0][k], temps[1][k], temps[2][k], temps[3][k], temps[4][k], part);
+#pragma unroll
+        for (int l = 0; l < (R ? R : RMAX); l++) { if (l >= rr) break; ip[k * rr + l] = part[l]; sum += part[l]; }
     }
-    const double correction = f[NS(Q, ic, jc)] - 1.0 / (double)(r * r) * sum;
-    for (int k = 0; k < r * r; k++) ip[k] += correction;
+    const double correction = f[NS(Q, ic, jc)] - 1.0 / (double)(rr * rr) * sum;
+#pragma unroll
+    for (int k = 0; k < (R ? R * R : RMAX * RMAX); k++) { if (k >= rr * rr) break; ip[k] += correction; }
+}
+// out receives the two sub-cell layers nearest the fine patch (2r values) for side d = 0..3
+template <int R>
+__device__ __forceinline__ void coarse_values_t(const VrtPatchDev& Q, int r, int i, int j, int d, int val, double* out) {
+    const int rr = R ? R : r;
+    double ip[RMAX * RMAX];
+    coarse_block_t<R>(Q, r, i, j, val, ip);
+#pragma unroll
+    for (int k = 0; k < (R ? R : RMAX); k++) {
+        if (k >= rr) break;
+        if (d == 0) { out[2 * k] = ip[rr * k + rr - 1]; out[2 * k + 1] = ip[rr * k + rr - 2]; }
+        else if (d == 1) { out[2 * k] = ip[k]; out[2 * k + 1] = ip[rr + k]; }
+        else if (d == 2) { out[2 * k] = ip[rr * k]; out[2 * k + 1] = ip[rr * k + 1]; }
+        else { out[2 * k] = ip[rr * (rr - 1) + k]; out[2 * k + 1] = ip[rr * (rr - 2) + k]; }
+    }
+}
+__device__ __forceinline__ void coarse_level_values(const VrtPatchDev& Q, int r, int i, int j, int d, int val, double* out) {
+    if (r == 2) coarse_values_t<2>(Q, r, i, j, d, val, out); else coarse_values_t<0>(Q, r, i, j, d, val, out);
+}
+// the same interpolation, all r x r sub-cells (GetWenoValueFromCoarseLevel with d = -1, used by the regrid data transfer)
+__device__ __forceinline__ void coarse_level_block(const VrtPatchDev& Q, int r, int i, int j, int val, double* ip) {
+    if (r == 2) coarse_block_t<2>(Q, r, i, j, val, ip); else coarse_block_t<0>(Q, r, i, j, val, ip);
 }
 
 // ---- regrid data movers: Mesh::InterMeshDataTransfer (Mesh.cpp:116-130) ---------------------------

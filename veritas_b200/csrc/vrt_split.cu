@@ -139,8 +139,18 @@ __global__ void k_commit(const VrtPatchDev* patches) { vrt_pdl_sync();
 __constant__ double c_IM[12] = {0.104166666666667, -0.708333333333334, 0.708333333333334, -0.104166666666667,
                                 0.117647058823529, 0.029411764705882,  0.029411764705882, 0.117647058823529,
                                 -0.083333333333333, 0.166666666666667, -0.166666666666667, 0.083333333333334};
-// one sub-cell k of GetInterpolantsREL (Rectangle.cpp:139-155) plus the mean-preserving correction (198-205)
-__device__ double rel_value(const VrtPatchDev& P, int i, int j, int k) {
+// sub-cell coefficients of GetInterpolantsREL (Rectangle.cpp:139-155) for sub-cell kk of rtb: they depend on (kk, rtb) only, so a
+// block tabulates them once in shared memory (same expressions, same bits) instead of re-deriving them — two fp64 divisions and
+// ~15 operations — for every sub-cell of every one of the three interpolations a cell needs
+constexpr int RTB_TAB = 32;
+__device__ __forceinline__ void rel_coefficients(int kk, int rtb, double& c0, double& c1, double& c2) {
+    double tl = -0.5 + kk / (double)rtb, tr = -0.5 + (kk + 1.0) / (double)rtb;
+    c0 = (tl + tr) * 0.5;
+    c1 = (tl * tl + tl * tr + tr * tr) / 3.0 - (1.0 / 12);
+    c2 = (tl * tl * tl + tl * tl * tr + tl * tr * tr + tr * tr * tr) * 0.25;
+}
+// one sub-cell k of GetInterpolantsREL plus the mean-preserving correction (Rectangle.cpp:198-205); tab = [3][RTB_TAB] or nullptr
+__device__ double rel_value(const VrtPatchDev& P, int i, int j, int k, const double* tab) {
     const int rtb = P.rtb;
     double f1 = P.f1[NS(P, i - 2, j)], f2 = P.f1[NS(P, i - 1, j)], f3 = P.f1[NS(P, i, j)], f4 = P.f1[NS(P, i + 1, j)], f5 = P.f1[NS(P, i + 2, j)];
     const double fc = f3;
@@ -150,10 +160,9 @@ __device__ double rel_value(const VrtPatchDev& P, int i, int j, int k) {
     double a3 = c_IM[8] * f1 + c_IM[9] * f2 + c_IM[10] * f4 + c_IM[11] * f5;
     double sum = 0.0, mine = 0.0;
     for (int kk = 0; kk < rtb; kk++) {
-        double tl = -0.5 + kk / (double)rtb, tr = -0.5 + (kk + 1.0) / (double)rtb;
-        double c0 = (tl + tr) * 0.5;
-        double c1 = (tl * tl + tl * tr + tr * tr) / 3.0 - (1.0 / 12);
-        double c2 = (tl * tl * tl + tl * tl * tr + tl * tr * tr + tr * tr * tr) * 0.25;
+        double c0, c1, c2;
+        if (tab) { c0 = tab[kk]; c1 = tab[RTB_TAB + kk]; c2 = tab[2 * RTB_TAB + kk]; }
+        else rel_coefficients(kk, rtb, c0, c1, c2);
         double v = c0 * a1 + c1 * a2 + c2 * a3 + f3;
         sum += v;
         if (kk == k) mine = v;
@@ -174,10 +183,14 @@ __global__ void __launch_bounds__(128) k_moments(const VrtPatchDev* patches, Sp 
     const int i = blockIdx.x / rtb, k = blockIdx.x % rtb;
     const double q = sp.q, c1 = sp.m_inv * VRT_C_INV, c2 = 1 / c1, c3 = 1 / 48.0;
     const double a2 = q * q * cell_a_sq(F, (i + P.x_pos) * rtb + k);
+    __shared__ double coef[3 * RTB_TAB];
+    const double* tab = rtb <= RTB_TAB ? coef : nullptr;
+    if (tab && (int)threadIdx.x < rtb) rel_coefficients(threadIdx.x, rtb, coef[threadIdx.x], coef[RTB_TAB + threadIdx.x], coef[2 * RTB_TAB + threadIdx.x]);
+    __syncthreads();
     double rho = 0.0, cur = 0.0;
     for (int j = threadIdx.x; j < P.n_p; j += blockDim.x) {
         if (P.flags[NS(P, i, j)] & VRT_NESTED) continue;   // cells covered by a finer patch (Rectangle.cpp:207-208)
-        double t0 = rel_value(P, i, j, k), tm1 = rel_value(P, i, j - 1, k), tp1 = rel_value(P, i, j + 1, k);
+        double t0 = rel_value(P, i, j, k, tab), tm1 = rel_value(P, i, j - 1, k, tab), tp1 = rel_value(P, i, j + 1, k, tab);
         double pm1 = momentum(P, sp, j - 1), p0 = momentum(P, sp, j), p1 = momentum(P, sp, j + 1), p2 = momentum(P, sp, j + 2);
         double um1 = gamma_(sp, pm1, a2) + c1 * pm1, u0 = gamma_(sp, p0, a2) + c1 * p0;
         double u1 = gamma_(sp, p1, a2) + c1 * p1, u2 = gamma_(sp, p2, a2) + c1 * p2;
