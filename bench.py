@@ -83,7 +83,15 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
-    def stop(self):
+    def mark(self):
+        """index of the next sample: brackets a region of interest inside a longer sampling run"""
+        return len(self.rows)
+
+    def stop(self, lo=None, hi=None):
+        """lo, hi = mark() at the start / end of the timed region.  The sampler is started before the warm-up (nvidia-smi needs up
+        to a second to deliver its first sample, longer than a 10-step timed region on 8 GPUs) and stopped after the end-to-end
+        loop; samples inside [lo, hi] are used if there are any, otherwise all samples of the run — warm-up, timed and end-to-end
+        steps, every one of them under the same load — and `window` says which."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -91,8 +99,14 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             pass
+        rows, window = self.rows, "whole run"
+        if lo is not None and hi is not None:
+            if hi > lo:
+                rows, window = self.rows[lo:hi], "timed region"
+            else:
+                rows, window = self.rows, "warm-up + timed + end-to-end steps (the timed region is shorter than nvidia-smi's first-sample latency)"
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for r in rows:
             p = [x.strip() for x in r.split(",")]
             if len(p) < 7:
                 continue
@@ -104,7 +118,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 
@@ -307,24 +321,25 @@ def main():
     q0 = species_charge()
 
     # ---- warm-up --------------------------------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     dt = run.calculate_dt()
     for _ in range(args.warmup):
         run.advance(dt)
     ctx.sync()
 
     # ---- device-resident throughput: K steps, CUDA events on the launching stream ----------------------------------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    mark_lo = sampler.mark()
     e0.record(stream)
     for _ in range(args.steps):
         run.advance(dt)
     e1.record(stream)
     barrier()
+    mark_hi = sampler.mark()
     ms = e0.elapsed_time(e1)
     launches = ctx.last_step_launches() * args.steps
-    clocks = sampler.stop()
     if dist is not None:
         tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -352,6 +367,7 @@ def main():
                 ctx.download_field(w, 0, buf)
     barrier()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop(mark_lo, mark_hi)
     if dist is not None:
         ts = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(ts, op=dist.ReduceOp.MAX)
