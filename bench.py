@@ -48,7 +48,7 @@ HOST_WORKLOADS = {
 
 
 # version of k_fused_stage the committed ncu traffic capture (profiles/fused_traffic.json) must match to be quoted as `traffic`
-FUSED_KERNEL_VERSION = "v17"
+FUSED_KERNEL_VERSION = "v18"
 
 
 def stage_bytes(cells_species, s):
