@@ -4,8 +4,18 @@
 // NCCL is bound at run time (dlopen) so that single-GPU use needs no NCCL at all and a host process that already
 // loaded a libnccl (e.g. torch's) shares it.
 #include "vrt_internal.cuh"
+#include <cstring>
 #include <dlfcn.h>
+#if defined(__has_include) && __has_include(<nccl.h>)
 #include <nccl.h>
+#else
+// No NCCL development header on this machine: the handful of declarations the dlopen'ed entry points need (NCCL's public ABI:
+// opaque communicator, 128-byte unique id, result / datatype enumerators), so that the library — single-GPU path included — still builds.
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef enum { ncclSuccess = 0 } ncclResult_t;
+typedef enum { ncclDouble = 8 } ncclDataType_t;
+#endif
 
 namespace {
 struct NcclApi {

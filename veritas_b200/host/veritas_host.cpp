@@ -28,6 +28,9 @@ Settings::Settings(const Input& grid, const Particles& particles, const Output& 
     auto fatal = [](const std::string& msg) { std::cerr << "ERROR: " << msg << std::endl; exit(EXIT_FAILURE); };
     if (refinementRatio % 2) fatal("Mesh refinement ratio 'refinementRatio' must be an even value.");
     if (x_size % refinementRatio != 0) fatal("'x_size' must be completely divisible by the Mesh refinement ratio 'refinementRatio'.");
+    // the regrid data path fills a one-coarse-cell ring = r fine ghost cells, and a patch has two ghost layers: the reference's own
+    // transfer code carries the same restriction (Rectangle.cpp:892-918); refuse instead of writing out of bounds
+    if (maxDepth >= 1 && refinementRatio != 2) fatal("a refined mesh (Lfinest > 1) needs 'refinementRatio' = 2: the regrid data transfer is written for that ratio.");
     for (unsigned int s = 0; s < p_size.size(); s++)
         if (p_size[s] % refinementRatio != 0)
             fatal("'p_size' at index (" + std::to_string(s) + ") must be completely divisible by the Mesh refinement ratio 'refinementRatio'.");
