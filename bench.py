@@ -230,6 +230,26 @@ def measure_fp64_peak():
         return float(json.load(open(os.path.join(ROOT, "profiles", "fp64_peak_r1.json")))["fp64_instr_per_s"]), "profiles/fp64_peak_r1.json (round 1)"
 
 
+def fused_vs_split_self_check(vb, S, np_, device):
+    """Pre-flight check of the kernels this run is about to time, on this device: 256 columns of the workload's own p grid (the
+    interior specialisation of the stage kernel and the long-column moments kernel), two free-running steps of the fused streaming
+    path against the bit-faithful split path (which the tests pin to the reference).  Aborts the bench if they disagree."""
+    import numpy as np
+    res = {}
+    for path in (S.PATH_SPLIT, S.PATH_FUSED):
+        run = vb.LaserPlasmaRun(256, np_, density=DENSITY, device=device, path=path)
+        run.init_device()
+        run.time = 3 * run.T
+        for _ in range(2):
+            run.advance(run.calculate_dt())
+        res[path] = [run.ctx.download_f(s, 0, 1) for s in range(2)] + [run.ctx.get_1d(S.J)]
+        run.ctx.close()
+    errs = [float(np.linalg.norm((b - a).ravel()) / max(np.linalg.norm(a.ravel()), 1e-300)) for a, b in zip(res[S.PATH_SPLIT], res[S.PATH_FUSED])]
+    if not (errs[0] < 1e-12 and errs[1] < 1e-12 and errs[2] < 1e-10):
+        raise SystemExit(f"bench.py: fused and split paths disagree on the pre-flight check ({errs}); the measurement is void")
+    return {"what": f"fused vs split path, 256x{np_}, 2 steps: relative L2 of f (e-, p+) and J", "rel_l2": errs}
+
+
 def cpu_baseline(budget_steps=6):
     harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
     nx, np_ = REF_SAMPLE
@@ -290,6 +310,8 @@ def main():
     if n_gpus > 1 and args.scaling == "weak":
         nx = WORKLOADS["c3"][0] * n_gpus
         wl = f"c3 per GPU ({nx}x{np_})"
+
+    self_check = fused_vs_split_self_check(vb, S, np_, local_rank) if rank == 0 else None
 
     run = vb.LaserPlasmaRun(nx, np_, density=DENSITY, device=local_rank, slab=(rank, n_gpus) if n_gpus > 1 else None,
                             graph=not args.no_graph)
@@ -493,7 +515,8 @@ def main():
             "roofline": roofline,
             "breakdown_ms_per_step": breakdown,
             "checks": {"finite": fields_ok, "particle_number_rel_drift": drift, "max_a_squared": a2max,
-                       "fields_phase_steps": fields_steps, "steps_run": run_steps, "state_hash": state_hash},
+                       "fields_phase_steps": fields_steps, "steps_run": run_steps, "state_hash": state_hash,
+                       "self_check": self_check},
             "cpu_baseline": cb,
         }
         print(json.dumps(out))

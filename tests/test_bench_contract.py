@@ -56,3 +56,25 @@ def test_reference_arm_on_an_amr_workload():
     d = json.loads(r.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and d["value"] > 1e5 and "3 levels" in d["config"]["workload"]
     assert d["cpu_baseline"]["same_config"] is True and d["cpu_baseline"]["kind"] == "reference"
+
+
+def test_committed_kernel_counts_and_traffic_describe_the_shipped_kernel():
+    """The fp64 roof of the bench line uses profiles/fused_sass_counts.json and `traffic` uses profiles/fused_traffic.json: both must
+    belong to the kernel version bench.py names, and the instruction counts must be those of the object that is actually built."""
+    import re
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sass_count
+    version = re.search(r'FUSED_KERNEL_VERSION = "(\w+)"', open(os.path.join(ROOT, "bench.py")).read()).group(1)
+    counts = json.load(open(os.path.join(ROOT, "profiles", "fused_sass_counts.json")))
+    traffic = json.load(open(os.path.join(ROOT, "profiles", "fused_traffic.json")))
+    assert counts["kernel_version"] == version and traffic["kernel_version"] == version
+    assert set(traffic["stages"]) >= {"0", "3", "5"}
+    obj = os.path.join(ROOT, "veritas_b200", "build", "vrt_fused.cu.o")
+    if not os.path.exists(obj):
+        pytest.skip("object not built")
+    for name, body in sass_count.functions(obj):
+        m = re.search(r"k_fused_stageILi(\d)ELi(\d)ELi128E", name)
+        if m:
+            r = sass_count.analyse(body, int(m.group(2)))
+            c = counts["stages"][f"S{m.group(1)}"]
+            assert abs(r["fp64_per_column"] - c["fp64_per_column"]) < 0.01 and abs(r["instr_per_column"] - c["instr_per_column"]) < 0.01, name

@@ -29,8 +29,9 @@ python tools/launch_summary.py gpurun_out/launches_$TAG.csv "python bench.py --s
 head -8 $P/launches_${TAG}_${KV}_summary.txt
 fi
 # launch list of the 3-level AMR workload through the host classes (what the step is made of)
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 3000 -c 1600 --csv --log-file gpurun_out/launches_c4_$TAG.csv oracle/_ref/host_harness /dev/null 512 64 3 0.1 12 regrid_every=22 time_only=1 warmup=2 > gpurun_out/launches_c4_bench_$TAG.log 2>&1
-python tools/launch_summary.py gpurun_out/launches_c4_$TAG.csv "host_harness 512 64 3 (config 4) under ncu --metrics gpu__time_duration.sum, 1600 launches from launch 3000 on" > $P/launches_c4_${TAG}_summary.txt 2>/dev/null
+# (pre_steps=0: no fields-only phase, so that the window lands in the Vlasov steps)
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 1500 -c 1200 --csv --log-file gpurun_out/launches_c4_$TAG.csv oracle/_ref/host_harness /dev/null 512 64 3 0.1 8 pre_steps=0 time_only=1 warmup=2 > gpurun_out/launches_c4_bench_$TAG.log 2>&1
+python tools/launch_summary.py gpurun_out/launches_c4_$TAG.csv "host_harness 512 64 3 (config 4), plasma phase, 1200 launches under ncu --metrics gpu__time_duration.sum" > $P/launches_c4_${TAG}_summary.txt 2>/dev/null
 head -40 $P/launches_c4_${TAG}_summary.txt
 for wl in c1 c2 c4; do
   timeout 600 python bench.py --workload $wl --steps 100 --warmup 5 > $P/bench_${wl}_$TAG.json 2> gpurun_out/bench_${wl}_$TAG.err; echo "bench $wl rc=$?"; cut -c1-400 $P/bench_${wl}_$TAG.json
