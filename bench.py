@@ -507,7 +507,7 @@ def main():
             "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{wl}: uniform {nx}x{np_} x-p mesh, single level, 2 species (e-, p+), laser-plasma case n={DENSITY} N_c, "
                                    f"t>=3T; inputs larger than L2 ({cells * 8 / 2**30:.1f} GiB per f plane pair)",
-                       "parallelism": f"x-slab x{n_gpus}" if n_gpus > 1 else "single GPU", "cuda_graph": not args.no_graph and n_gpus == 1},
+                       "parallelism": f"x-slab x{n_gpus}" if n_gpus > 1 else "single GPU", "cuda_graph": (not args.no_graph) and (n_gpus == 1 or os.environ.get("VRT_MULTI_GRAPH", "1") != "0")},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "CalculateDt + Advance + 1-D output arrays per step through the C ABI with host buffers; f stays resident as in the reference"},

@@ -26,7 +26,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nx, np_, steps = int(os.environ.get("VRT_CHECK_NX", 512)), int(os.environ.get("VRT_CHECK_NP", 192)), 4
     ok = True
-    for graph in (False,):
+    for graph in (False, True):
         runs = {}
         for mode in ("slab", "full"):
             run = vb.LaserPlasmaRun(nx, np_, density=0.3, device=local, slab=(rank, world) if mode == "slab" else None, graph=graph)

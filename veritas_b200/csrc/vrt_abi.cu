@@ -824,7 +824,11 @@ int vrt_step(vrt_ctx* c, double dt, const double laser[12]) {
     int key = 0;
     for (auto& S : c->S) if (S.path == VRT_PATH_FUSED) { key = S.i_f0; if (!check(c, S.i_f0 == S.i_f1, "vrt_step: mid-step state")) return VRT_ERR_STATE; }
     for (auto& S : c->S) if (S.path == VRT_PATH_FUSED && !check(c, S.i_f0 == key, "vrt_step: species out of phase")) return VRT_ERR_STATE;
-    const bool use_graph = c->use_graph && c->n_ranks == 1;
+    // x-slab runs: the step's NCCL calls (grouped send/recv, all-gather) sit on the communication stream between events of the
+    // compute streams and are captured with it (NCCL >= 2.9 is capturable; every rank captures the same sequence).  VRT_MULTI_GRAPH=0
+    // issues the step eagerly instead.
+    static const bool multi_graph = !(getenv("VRT_MULTI_GRAPH") && atoi(getenv("VRT_MULTI_GRAPH")) == 0);
+    const bool use_graph = c->use_graph && (c->n_ranks == 1 || multi_graph);
     if (!use_graph) {
         if (int r = enqueue_step(c)) return r;
         c->last_step_launches = c->launches - l0;
