@@ -288,15 +288,20 @@ __global__ void k_commit_ex0(VrtFields F) { vrt_pdl_sync(); F.Ex0[0] = F.Ex0[1];
 // step is a chain of latency-bound launches and these seven are on its critical path): one CTA runs the same five passes over the
 // tiles in turn — the same per-tile arithmetic and the same fixed-order sums of tile partials as the multi-CTA kernels, hence the
 // same bits — then tabulates E and commits Ex0.
+// The three N-vectors the passes hand to each other (b, z, prefix of z) and sum(b) live in shared memory here (3N + 1 doubles,
+// <= 96 KB) instead of the global scratch: a single CTA would otherwise pay a global-memory round trip between every pair of passes.
 constexpr int PSMALL = 4;
 __global__ void __launch_bounds__(PTHR) k_poisson_small(VrtFields F, double* part, int G) {
     vrt_pdl_sync();
+    extern __shared__ __align__(16) double psm[];
+    F.scratch = psm;
+    part = psm + 3L * F.N + 8;            // the tile partials of the four passes too (PSMALL entries each)
     for (int blk = 0; blk < G; blk++) d_poisson_rhs(F, part, blk);
     __syncthreads();
-    for (int blk = 0; blk < G; blk++) { d_poisson_conv(F, part, part + PMAXT, G, blk); __syncthreads(); }
-    for (int blk = 0; blk < G; blk++) { d_poisson_scan1(F, part + PMAXT, part + 2 * PMAXT, G, blk); __syncthreads(); }
-    for (int blk = 0; blk < G; blk++) { d_poisson_dsum(F, part + 2 * PMAXT, part + 3 * PMAXT, G, blk); __syncthreads(); }
-    for (int blk = 0; blk < G; blk++) { d_poisson_scan2(F, part + 2 * PMAXT, part + 3 * PMAXT, G, blk); __syncthreads(); }
+    for (int blk = 0; blk < G; blk++) { d_poisson_conv(F, part, part + 8, G, blk); __syncthreads(); }
+    for (int blk = 0; blk < G; blk++) { d_poisson_scan1(F, part + 8, part + 16, G, blk); __syncthreads(); }
+    for (int blk = 0; blk < G; blk++) { d_poisson_dsum(F, part + 16, part + 24, G, blk); __syncthreads(); }
+    for (int blk = 0; blk < G; blk++) { d_poisson_scan2(F, part + 16, part + 24, G, blk); __syncthreads(); }
     __shared__ double ex0_new;
     if (threadIdx.x == 0) {
         const double ex0 = *F.Ex0;
@@ -381,7 +386,11 @@ int vrt_fields_poisson(vrt_ctx* c) {
     double* part = F.scratch + 3L * F.N + 8;      // 4 arrays of PMAXT tile partials behind the three N-vectors and sum(b)
     const bool small_ok = !(getenv("VRT_POISSON_SMALL") && atoi(getenv("VRT_POISSON_SMALL")) == 0);     // 0: the multi-CTA passes (tests)
     if (G <= PSMALL && small_ok) {
-        vrt_launch(k_poisson_small, dim3(1), dim3(PTHR), c->stream, F, part, G);
+        const size_t smem = sizeof(double) * (3 * (size_t)F.N + 8 + 32);
+        static bool attr_dev[64] = {};
+        bool& attr = attr_dev[c->device & 63];
+        if (!attr) { VRT_CUDA(c, cudaFuncSetAttribute(k_poisson_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (3 * PSMALL * PTILE + 8 + 32)))); attr = true; }
+        vrt_launch_smem(k_poisson_small, dim3(1), dim3(PTHR), smem, c->stream, F, part, G);
         c->launches += 1;
         VRT_CUDA(c, cudaGetLastError());
         return 0;

@@ -20,12 +20,16 @@ inline bool vrt_pdl_enabled() {            // VRT_PDL=0: plain stream-ordered la
 }
 
 template <typename... KArgs, typename... Args>
-inline cudaError_t vrt_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args&&... args) {
+inline cudaError_t vrt_launch_smem(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = vrt_pdl_enabled() ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t vrt_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args&&... args) {
+    return vrt_launch_smem(kernel, grid, block, 0, stream, std::forward<Args>(args)...);
 }

@@ -64,8 +64,11 @@ __global__ void k_fluxes(const VrtPatchDev* patches, int step) { vrt_pdl_sync();
         if (step == 0) P.FpL[c] = dp_inv * ((am > 0.0 ? P.f1[c - 1] : P.f1[c]) * am);
     }
 }
-// sub-step 0, part 3: RK combination over the whole padded array (Rectangle.cpp:1396-1517)
-__global__ void k_rk_combine(const VrtPatchDev* patches, int step, const double* d_dt) { vrt_pdl_sync();
+// sub-step 0, parts 3 + 4 in one launch: the RK combination of every padded face (Rectangle.cpp:1396-1517) and, for interior cells, the
+// low-order predictor f2 = f0 + FLS in gather form (Rectangle.cpp:1518-1534; quirks Q11, Q14: the reference's summation order).  The predictor needs FLS at the cell's own and its upper neighbours' faces; FLS = (sum_k a_sk) dt FL
+// is one multiplication of a plane that is final before this kernel starts, so the neighbours' values are formed here again (the
+// same product, the same bits) instead of being read back after a grid-wide dependency — one launch less on the chain.
+__global__ void k_rk_combine_apply(const VrtPatchDev* patches, int step, const double* d_dt) { vrt_pdl_sync();
     PATCH_THREAD_SETUP
     const double timestep = *d_dt;
     double a[6], aSum = 0.0;
@@ -75,31 +78,32 @@ __global__ void k_rk_combine(const VrtPatchDev* patches, int step, const double*
     for (int k = 1; k <= step; k++) { sx = sx + a[k] * P.FxH[k * P.npad + c]; sp_ = sp_ + a[k] * P.FpH[k * P.npad + c]; }
     P.FxLS[c] = xl; P.FpLS[c] = pl;
     P.FxDS[c] = sx - xl; P.FpDS[c] = sp_ - pl;
+    if (i < 0 || i >= nx || j < 0 || j >= np) return;
+    const int xm = P.left ? 1 : 0, xp = P.right ? nx : nx + 1, pp = P.up ? np : np + 1, pm = P.down ? 1 : 0;
+    const long cxp = c + P.pitch;
+    const bool in_i = (i >= xm && i < xp), in_j = (j >= pm && j < pp);
+    const bool in_j1 = (j + 1 >= pm && j + 1 < pp), in_i1 = (i + 1 >= xm && i + 1 < xp);
+    double v = P.f0[c];
+    if (in_i && in_j) { v += xl; v += pl; }
+    if (in_i && in_j1) v -= aSum * P.FpL[c + 1];
+    if (in_i1 && in_j) v -= aSum * P.FxL[cxp];
+    P.f2[c] = v;
 }
 
-// flux application in gather form, same summation order as the reference's serial scatter
-// (Rectangle.cpp:1518-1534 / 1595-1612; quirks Q11, Q14).  mode 0: f2 = f0 + FLS;  mode 1: f1 = f2 + C*FDS.
-__global__ void k_apply(const VrtPatchDev* patches, int mode) { vrt_pdl_sync();
+// sub-step 2: f1 = f2 + C FDS in gather form, same summation order as the reference's serial scatter (Rectangle.cpp:1595-1612;
+// quirks Q11, Q14)
+__global__ void k_apply(const VrtPatchDev* patches) { vrt_pdl_sync();
     PATCH_THREAD_SETUP
     if (i < 0 || i >= nx || j < 0 || j >= np) return;
     const int xm = P.left ? 1 : 0, xp = P.right ? nx : nx + 1, pp = P.up ? np : np + 1, pm = P.down ? 1 : 0;
     const long cxp = c + P.pitch;
     const bool in_i = (i >= xm && i < xp), in_j = (j >= pm && j < pp);
     const bool in_j1 = (j + 1 >= pm && j + 1 < pp), in_i1 = (i + 1 >= xm && i + 1 < xp);
-    double v;
-    if (mode == 0) {
-        v = P.f0[c];
-        if (in_i && in_j) { v += P.FxLS[c]; v += P.FpLS[c]; }
-        if (in_i && in_j1) v -= P.FpLS[c + 1];
-        if (in_i1 && in_j) v -= P.FxLS[cxp];
-        P.f2[c] = v;
-    } else {
-        v = P.f2[c];
-        if (in_i && in_j) { v += P.Cx[c] * P.FxDS[c]; v += P.Cp[c] * P.FpDS[c]; }
-        if (in_i && in_j1) v -= P.Cp[c + 1] * P.FpDS[c + 1];
-        if (in_i1 && in_j) v -= P.Cx[cxp] * P.FxDS[cxp];
-        P.f1[c] = v;
-    }
+    double v = P.f2[c];
+    if (in_i && in_j) { v += P.Cx[c] * P.FxDS[c]; v += P.Cp[c] * P.FpDS[c]; }
+    if (in_i && in_j1) v -= P.Cp[c + 1] * P.FpDS[c + 1];
+    if (in_i1 && in_j) v -= P.Cx[cxp] * P.FxDS[cxp];
+    P.f1[c] = v;
 }
 
 // sub-step 1: Zalesak ratios R+- on [-1,n_x]x[-1,n_p] (Rectangle.cpp:1536-1579)
@@ -313,15 +317,14 @@ int vrt_split_substep(vrt_ctx* c, int s, int depth, const double* d_dt, int step
         vrt_launch(k_fluxes, dim3(grid), dim3(256), c->stream, tab, step);
         c->launches += 2;
         if (int r = vrt_amr_level_boundary_fluxes(c, s, depth, step)) return r;
-        vrt_launch(k_rk_combine, dim3(grid), dim3(256), c->stream, tab, step, d_dt);
-        vrt_launch(k_apply, dim3(grid), dim3(256), c->stream, tab, 0);
-        c->launches += 2;
+        vrt_launch(k_rk_combine_apply, dim3(grid), dim3(256), c->stream, tab, step, d_dt);
+        c->launches += 1;
     } else if (substep == 1) {
         vrt_launch(k_limiter_r, dim3(grid), dim3(256), c->stream, tab);
         vrt_launch(k_limiter_c, dim3(grid), dim3(256), c->stream, tab);
         c->launches += 2;
     } else if (substep == 2) {
-        vrt_launch(k_apply, dim3(grid), dim3(256), c->stream, tab, 1);
+        vrt_launch(k_apply, dim3(grid), dim3(256), c->stream, tab);
         c->launches += 1;
     } else if (substep == 3) {
         vrt_launch(k_commit, dim3(grid), dim3(256), c->stream, tab);
@@ -353,15 +356,14 @@ int vrt_split_substep_all(vrt_ctx* c, int s, const double* d_dt, int step, int s
         vrt_launch(k_fluxes, dim3(grid), dim3(256), c->stream, tab, step);
         c->launches += 2;
         if (int r = vrt_amr_level_boundary_fluxes_all(c, s, step)) return r;
-        vrt_launch(k_rk_combine, dim3(grid), dim3(256), c->stream, tab, step, d_dt);
-        vrt_launch(k_apply, dim3(grid), dim3(256), c->stream, tab, 0);
-        c->launches += 2;
+        vrt_launch(k_rk_combine_apply, dim3(grid), dim3(256), c->stream, tab, step, d_dt);
+        c->launches += 1;
     } else if (substep == 1) {
         vrt_launch(k_limiter_r, dim3(grid), dim3(256), c->stream, tab);
         vrt_launch(k_limiter_c, dim3(grid), dim3(256), c->stream, tab);
         c->launches += 2;
     } else if (substep == 2) {
-        vrt_launch(k_apply, dim3(grid), dim3(256), c->stream, tab, 1);
+        vrt_launch(k_apply, dim3(grid), dim3(256), c->stream, tab);
         c->launches += 1;
     } else {
         vrt_launch(k_commit, dim3(grid), dim3(256), c->stream, tab);
