@@ -585,15 +585,59 @@ static int ready_species(vrt_ctx* c, int s) {
     return 0;
 }
 
+static int species_moment_kernel(vrt_ctx* c, int s) {
+    return (c->S[s].path == VRT_PATH_FUSED) ? vrt_fused_moments(c, s) : vrt_split_moments(c, s);
+}
+
+// fn(s) for every species: species s > 0 on its own stream between a fork and a join event (concurrent branches of the step graph),
+// species 0 on the context's stream.  fn enqueues on c->stream.
+extern "C++" {
+template <typename Fn>
+static int for_each_species_forked(vrt_ctx* c, Fn fn) {
+    int r;
+    const bool fork = c->fork_species && c->n_species > 1;
+    if (!fork) {
+        for (int s = 0; s < c->n_species; s++) if ((r = fn(s))) return r;
+        return 0;
+    }
+    if (!c->ev_fork) {
+        VRT_CUDA(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        c->aux_stream.resize(c->n_species - 1); c->aux_join.resize(c->n_species - 1);
+        for (int s = 1; s < c->n_species; s++) {
+            VRT_CUDA(c, cudaStreamCreateWithFlags(&c->aux_stream[s - 1], cudaStreamNonBlocking));
+            VRT_CUDA(c, cudaEventCreateWithFlags(&c->aux_join[s - 1], cudaEventDisableTiming));
+        }
+    }
+    cudaStream_t main_stream = c->stream;
+    VRT_CUDA(c, cudaEventRecord(c->ev_fork, main_stream));
+    for (int s = 1; s < c->n_species; s++) {
+        cudaStream_t aux = c->aux_stream[s - 1];
+        VRT_CUDA(c, cudaStreamWaitEvent(aux, c->ev_fork, 0));
+        c->stream = aux;
+        r = fn(s);
+        c->stream = main_stream;
+        if (r) return r;
+        VRT_CUDA(c, cudaEventRecord(c->aux_join[s - 1], aux));
+    }
+    if ((r = fn(0))) return r;
+    for (int s = 1; s < c->n_species; s++) VRT_CUDA(c, cudaStreamWaitEvent(main_stream, c->aux_join[s - 1], 0));
+    return 0;
+}
+}  // extern "C++"
+
+// EMFieldSolver::AssembleRhoAndJ (EMSolver.cpp:104-122): the species' moment kernels on concurrent branches (they only write their own
+// per-patch / per-slab arrays), then ONE assembly launch that forms charges[s], J and the total charge in the reference's order of
+// additions; on x-slab runs the slabs are gathered in between and the total follows the gather
 static int moments_impl(vrt_ctx* c) {
     int r;
-    if ((r = vrt_fields_assemble_begin(c))) return r;
-    for (int s = 0; s < c->n_species; s++) {
-        r = (c->S[s].path == VRT_PATH_FUSED) ? vrt_fused_moments(c, s) : vrt_split_moments(c, s);
-        if (r) return r;
+    if ((r = for_each_species_forked(c, [&](int s) { return species_moment_kernel(c, s); }))) return r;
+    const unsigned all = (1u << c->n_species) - 1u;
+    if ((r = vrt_fields_assemble(c, all, c->n_ranks == 1))) return r;
+    if (c->n_ranks > 1) {
+        if ((r = vrt_comm_gather_moments(c))) return r;
+        if ((r = vrt_fields_total_charge(c))) return r;
     }
-    if (c->n_ranks > 1 && (r = vrt_comm_gather_moments(c))) return r;
-    return vrt_fields_assemble_end(c);
+    return 0;
 }
 
 int vrt_moments(vrt_ctx* c) { if (int r = ready(c)) return r; return moments_impl(c); }
@@ -605,9 +649,8 @@ int vrt_moments_species(vrt_ctx* c, int s, double* charge_host, double* j_host) 
     // the species' contribution alone: charges[s] and the total current are rebuilt from this species only, copied out,
     // and the assembled state (all species) is restored by a full vrt_moments afterwards
     int r;
-    if ((r = vrt_fields_assemble_begin(c))) return r;
-    r = (c->S[s].path == VRT_PATH_FUSED) ? vrt_fused_moments(c, s) : vrt_split_moments(c, s);
-    if (r) return r;
+    if ((r = species_moment_kernel(c, s))) return r;
+    if ((r = vrt_fields_assemble(c, 1u << s, 0))) return r;
     const int N = c->F.N;
     std::vector<double> a(N), b(N);
     VRT_CUDA(c, cudaMemcpyAsync(a.data(), c->S[s].d_charges, sizeof(double) * N, cudaMemcpyDeviceToHost, c->stream));
@@ -627,9 +670,7 @@ int vrt_patch_moments(vrt_ctx* c, int s, int patch, double* charge_r_host, doubl
     // the species' moment kernels also rebuild charges[s] and J from this species alone (as in vrt_moments_species); the
     // assembled state of all species is restored by a full vrt_moments afterwards
     int r;
-    if ((r = vrt_fields_assemble_begin(c))) return r;
-    r = (S.path == VRT_PATH_FUSED) ? vrt_fused_moments(c, s) : vrt_split_moments(c, s);
-    if (r) return r;
+    if ((r = species_moment_kernel(c, s))) return r;
     const double *d_charge, *d_current;
     size_t n;
     if (S.path == VRT_PATH_FUSED) { d_charge = S.slab.chargeR; d_current = S.slab.currentR; n = (size_t)S.slab.n_x; }
@@ -750,35 +791,8 @@ double vrt_update_time(double time, int step, double dt) {   // Settings::Update
 // species s > 0 is enqueued on its own stream between a fork and a join event: concurrent branches of the step graph.  This
 // halves the launch-latency-bound time of small and AMR hierarchies and fills the tail of the last wave of large kernels.
 static int vlasov_stages_all(vrt_ctx* c, int i) {
-    int r;
     // (x-slab runs too: the NCCL calls all go to the communication stream, in host order, whichever stream computes)
-    const bool fork = c->fork_species && c->n_species > 1;
-    if (!fork) {
-        for (int s = 0; s < c->n_species; s++) if ((r = vlasov_stage_impl(c, s, &c->d_params->dt, i))) return r;
-        return 0;
-    }
-    if (!c->ev_fork) {
-        VRT_CUDA(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-        c->aux_stream.resize(c->n_species - 1); c->aux_join.resize(c->n_species - 1);
-        for (int s = 1; s < c->n_species; s++) {
-            VRT_CUDA(c, cudaStreamCreateWithFlags(&c->aux_stream[s - 1], cudaStreamNonBlocking));
-            VRT_CUDA(c, cudaEventCreateWithFlags(&c->aux_join[s - 1], cudaEventDisableTiming));
-        }
-    }
-    cudaStream_t main_stream = c->stream;
-    VRT_CUDA(c, cudaEventRecord(c->ev_fork, main_stream));
-    for (int s = 1; s < c->n_species; s++) {
-        cudaStream_t aux = c->aux_stream[s - 1];
-        VRT_CUDA(c, cudaStreamWaitEvent(aux, c->ev_fork, 0));
-        c->stream = aux;
-        r = vlasov_stage_impl(c, s, &c->d_params->dt, i);
-        c->stream = main_stream;
-        if (r) return r;
-        VRT_CUDA(c, cudaEventRecord(c->aux_join[s - 1], aux));
-    }
-    if ((r = vlasov_stage_impl(c, 0, &c->d_params->dt, i))) return r;
-    for (int s = 1; s < c->n_species; s++) VRT_CUDA(c, cudaStreamWaitEvent(main_stream, c->aux_join[s - 1], 0));
-    return 0;
+    return for_each_species_forked(c, [&](int s) { return vlasov_stage_impl(c, s, &c->d_params->dt, i); });
 }
 
 // the six stages of SolverManager::Advance as stream work (SolverManager.cpp:28-39)

@@ -336,18 +336,46 @@ __global__ void k_cfl(VrtFields F, CflSpecies sp) {
 __global__ void k_cfl_finish(VrtFields F) { double pc = *F.cfl; F.cfl[1] = 1.0 / fmax((VRT_CS / F.dx + pc), 1e-40); }
 
 // ---- AssembleRhoAndJ bookkeeping (EMSolver.cpp:104-122, Level.cpp:19-62) -----------------------------
-__global__ void k_zero2(double* a, double* b, int n) { vrt_pdl_sync();
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { a[i] = 0.0; if (b) b[i] = 0.0; }
+// EMFieldSolver::AssembleRhoAndJ (EMSolver.cpp:104-122) after the species' moment kernels, one thread per finest column: for every
+// species in turn  charges[s][i] = 0 + (slab value | level sums from the finest level down, each level the sum over its patches in
+// table order: Level::CollectRhoAndJ, Level.cpp:42-62, then Mesh::InterpolateRhoAndJToFinestMesh, Mesh.cpp:52-56),  J[i] carried
+// across the species in the same order,  charge[i] = 0 + charges[0][i] + charges[1][i] + ...  — the additions of the reference's loops
+// in their order, in one launch instead of three clears, one add per species and level set, and one total per species.
+__global__ void k_assemble(VrtAssembleArgs A) { vrt_pdl_sync();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.N) return;
+    double cu = 0.0, tot = 0.0;
+    for (int s = 0; s < A.n_species; s++) {
+        const VrtAssembleSpecies& S = A.sp[s];
+        double ch = 0.0;
+        if (S.mode == 0) {
+            const int k = i - S.x0;
+            if (k >= 0 && k < S.n) { ch += S.chargeR[k]; cu += S.currentR[k]; }
+        } else {
+            for (int d = 0; d < S.n_levels; d++) {
+                if (!S.count[d]) continue;
+                double lc = 0.0, lj = 0.0;
+                for (int p = S.first[d]; p < S.first[d] + S.count[d]; p++) {
+                    const VrtPatchDev& P = S.all[p];
+                    const int k = i - P.x_pos * P.rtb;
+                    if (k >= 0 && k < P.n_x * P.rtb) { lc += P.chargeR[k]; lj += P.currentR[k]; }
+                }
+                ch += lc; cu += lj;
+            }
+        }
+        S.charges[i] = ch;
+        tot += ch;
+    }
+    A.J[i] = cu;
+    if (A.total) A.charge[i] = tot;
 }
-// charges[s][x0+i] (+)= chargeR[i]; J[x0+i] += currentR[i]
-__global__ void k_add_moments(double* charges, double* J, const double* chargeR, const double* currentR, int x0, int n) { vrt_pdl_sync();
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { charges[x0 + i] += chargeR[i]; J[x0 + i] += currentR[i]; }
-}
-__global__ void k_add1(double* dst, const double* src, int n) { vrt_pdl_sync();
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] += src[i];
+struct ChargePtrs { int n; const double* p[8]; };
+__global__ void k_total_charge(ChargePtrs C, double* charge, int N) { vrt_pdl_sync();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double tot = 0.0;
+    for (int s = 0; s < C.n; s++) tot += C.p[s][i];
+    charge[i] = tot;
 }
 __global__ void k_neutralize(VrtFields F) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -432,28 +460,33 @@ int vrt_fields_cfl(vrt_ctx* c) {
     return 0;
 }
 
-int vrt_fields_assemble_begin(vrt_ctx* c) {
-    VrtFields& F = c->F;
-    vrt_launch(k_zero2, dim3(grid1(F.N)), dim3(256), c->stream, F.charge, F.J, F.N);
-    c->launches += 1;
+int vrt_fields_assemble(vrt_ctx* c, unsigned mask, int total) {
+    VrtAssembleArgs A{};
+    A.N = c->F.N; A.total = total; A.J = c->F.J; A.charge = c->F.charge;
     for (int s = 0; s < c->n_species; s++) {
-        vrt_launch(k_zero2, dim3(grid1(F.N)), dim3(256), c->stream, c->S[s].d_charges, nullptr, F.N);
-        c->launches += 1;
+        if (!((mask >> s) & 1u)) continue;
+        const VrtSpeciesState& S = c->S[s];
+        VrtAssembleSpecies& T = A.sp[A.n_species++];
+        T.charges = S.d_charges;
+        if (S.path == VRT_PATH_FUSED) {
+            T.mode = 0; T.chargeR = S.slab.chargeR; T.currentR = S.slab.currentR; T.x0 = S.slab.x_begin; T.n = S.slab.n_x;
+        } else {
+            T.mode = 1; T.all = S.d_patches; T.n_levels = (int)S.level_patches.size();
+            if (T.n_levels > 16) { c->err = "vrt_moments: more than 16 levels"; return VRT_ERR_ARG; }
+            for (int d = 0; d < T.n_levels; d++) { T.count[d] = (int)S.level_patches[d].size(); T.first[d] = T.count[d] ? S.level_patches[d][0] : 0; }
+        }
     }
+    vrt_launch(k_assemble, dim3(grid1(A.N)), dim3(256), c->stream, A);
+    c->launches += 1;
     VRT_CUDA(c, cudaGetLastError());
     return 0;
 }
-int vrt_fields_assemble_add(vrt_ctx* c, int s, const double* chargeR, const double* currentR, int x0, int n) {
-    vrt_launch(k_add_moments, dim3(grid1(n)), dim3(256), c->stream, c->S[s].d_charges, c->F.J, chargeR, currentR, x0, n);
+int vrt_fields_total_charge(vrt_ctx* c) {
+    ChargePtrs C{};
+    C.n = c->n_species;
+    for (int s = 0; s < c->n_species; s++) C.p[s] = c->S[s].d_charges;
+    vrt_launch(k_total_charge, dim3(grid1(c->F.N)), dim3(256), c->stream, C, c->F.charge, c->F.N);
     c->launches += 1;
-    VRT_CUDA(c, cudaGetLastError());
-    return 0;
-}
-int vrt_fields_assemble_end(vrt_ctx* c) {
-    for (int s = 0; s < c->n_species; s++) {
-        vrt_launch(k_add1, dim3(grid1(c->F.N)), dim3(256), c->stream, c->F.charge, c->S[s].d_charges, c->F.N);
-        c->launches += 1;
-    }
     VRT_CUDA(c, cudaGetLastError());
     return 0;
 }

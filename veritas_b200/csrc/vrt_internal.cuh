@@ -43,6 +43,17 @@ struct VrtFields {
     double* cfl;                // device scalar (max-reduction result)
 };
 
+// what the assembly kernel needs to know about one species' moments
+struct VrtAssembleSpecies {
+    int mode;                          // 0: slab arrays, 1: patch table
+    const double *chargeR, *currentR;  // mode 0: the slab's columns [x0, x0 + n)
+    int x0, n;
+    const struct VrtPatchDev* all;     // mode 1: device patch table and its level ranges (finest first)
+    int n_levels, first[16], count[16];
+    double* charges;                   // out: N entries
+};
+struct VrtAssembleArgs { int n_species, N, total; VrtAssembleSpecies sp[8]; double* J; double* charge; };
+
 // Species constants (Settings.hpp:39-41)
 struct VrtSpecies {
     double m, q, pmin, dp_finest;
@@ -194,7 +205,7 @@ void vrt_invalidate_hierarchies(vrt_ctx* c);
 // split path (vrt_split.cu, compiled with -fmad=false)
 int vrt_split_substep(vrt_ctx* c, int s, int depth, const double* d_dt, int step, int substep);
 int vrt_split_substep_all(vrt_ctx* c, int s, const double* d_dt, int step, int substep);
-int vrt_split_moments(vrt_ctx* c, int s);
+int vrt_split_moments(vrt_ctx* c, int s);      // the species' per-patch kernel only (chargeR / currentR of every patch)
 int vrt_split_patch_energy(vrt_ctx* c, int s, int patch, double* host_energy);
 // AMR kernels (vrt_amr.cu, compiled with -fmad=false)
 int vrt_amr_upload_connectivity(vrt_ctx* c, int s, const vrt_conn& C);
@@ -208,13 +219,15 @@ int vrt_amr_error_flags(vrt_ctx* c, int s, int patch, const double weights[5], d
 int vrt_fields_rhs_update_faces(vrt_ctx* c, int step, const VrtStepParams* d_params, double* asq_out = nullptr);
 int vrt_fields_poisson(vrt_ctx* c);
 int vrt_fields_cfl(vrt_ctx* c);
-int vrt_fields_assemble_begin(vrt_ctx* c);
-int vrt_fields_assemble_add(vrt_ctx* c, int s, const double* chargeR, const double* currentR, int x0, int n);
-int vrt_fields_assemble_end(vrt_ctx* c);
+// EMFieldSolver::AssembleRhoAndJ (EMSolver.cpp:104-122) behind the species' moment kernels: ONE launch forms, per finest column,
+// charges[s] of every species in `mask` (bit s), the current J accumulated over those species in species order, and (total != 0)
+// charge = sum of the species charges — each from zero, with the additions and their order of the reference's loops
+int vrt_fields_assemble(vrt_ctx* c, unsigned mask, int total);
+int vrt_fields_total_charge(vrt_ctx* c);      // charge = sum_s charges[s] (x-slab runs: after the all-gather)
 int vrt_fields_neutralize(vrt_ctx* c);
 // fused path (vrt_fused.cu)
 int vrt_fused_stage(vrt_ctx* c, int s, const double* d_dt, int step);
-int vrt_fused_moments(vrt_ctx* c, int s);
+int vrt_fused_moments(vrt_ctx* c, int s);      // the species' slab kernel only (chargeR / currentR of the slab's columns)
 int vrt_fused_zero_ghosts(vrt_ctx* c, int s, int plane_idx);
 int vrt_fused_make_maps(vrt_ctx* c, int s);
 int vrt_fused_plan_impl(vrt_ctx* c, int s, int out[6]);

@@ -373,30 +373,8 @@ int vrt_split_substep_all(vrt_ctx* c, int s, const double* d_dt, int step, int s
     return 0;
 }
 
-// Mesh::InterpolateRhoAndJToFinestMesh (Mesh.cpp:52-56): per level, patch moments are summed into a level array
-// (Level::CollectRhoAndJ, Level.cpp:42-62) which is then added to the species charge and the total current
-// Level::CollectRhoAndJ + the per-level additions of Mesh::InterpolateRhoAndJToFinestMesh for all levels in one pass: thread i
-// (finest x index) forms, level by level from the finest, the level sum over the patches covering i in table (= rectangle)
-// order and adds it to the species charge and the total current — the additions and their order are those of the reference's
-// per-level loops (chargeL = sum over rectangles, then charges += chargeL).
-struct LevelRanges { int n_levels; int first[16]; int count[16]; };
-__global__ void k_collect_moments(const VrtPatchDev* all, LevelRanges R, double* charges, double* J, int N) { vrt_pdl_sync();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    double ch = charges[i], cu = J[i];
-    for (int d = 0; d < R.n_levels; d++) {
-        if (!R.count[d]) continue;
-        double lc = 0.0, lj = 0.0;
-        for (int p = R.first[d]; p < R.first[d] + R.count[d]; p++) {
-            const VrtPatchDev& P = all[p];
-            const int k = i - P.x_pos * P.rtb;
-            if (k >= 0 && k < P.n_x * P.rtb) { lc += P.chargeR[k]; lj += P.currentR[k]; }
-        }
-        ch += lc; cu += lj;
-    }
-    charges[i] = ch; J[i] = cu;
-}
-
+// the species' patch moments (Rectangle::chargeR / currentR of every patch); the level sums and the species / total assembly are
+// k_assemble's (vrt_fields.cu)
 int vrt_split_moments(vrt_ctx* c, int s) {
     VrtSpeciesState& S = c->S[s];
     if (S.table.empty()) return 0;
@@ -404,12 +382,7 @@ int vrt_split_moments(vrt_ctx* c, int s) {
     int mx = 0;
     for (const VrtPatchDev& T : S.table) mx = std::max(mx, T.n_x * T.rtb);
     vrt_launch(k_moments, dim3(dim3(mx, (unsigned)S.table.size())), dim3(128), c->stream, S.d_patches, sp, c->F);
-    LevelRanges R{};
-    R.n_levels = (int)S.level_patches.size();
-    if (R.n_levels > 16) { c->err = "vrt_moments: more than 16 levels"; return VRT_ERR_ARG; }
-    for (int d = 0; d < R.n_levels; d++) { R.count[d] = (int)S.level_patches[d].size(); R.first[d] = R.count[d] ? S.level_patches[d][0] : 0; }
-    vrt_launch(k_collect_moments, dim3((c->F.N + 255) / 256), dim3(256), c->stream, S.d_patches, R, S.d_charges, c->F.J, c->F.N);
-    c->launches += 2;
+    c->launches += 1;
     VRT_CUDA(c, cudaGetLastError());
     return 0;
 }
