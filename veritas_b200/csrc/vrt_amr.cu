@@ -665,7 +665,8 @@ int vrt_amr_push_data(vrt_ctx* c, int s, int val) {
 int vrt_amr_push_boundary_c(vrt_ctx* c, int s) {
     const int nl = (int)c->S[s].level_patches.size();
     if (int rc = vrt_amr_level_pass(c, s, -1, 4, 1)) return rc;
-    for (int l = 0; l < nl; l++) if (int rc = vrt_amr_level_pass(c, s, l, 5, 1)) return rc;
+    // (the coarsest level has no coarser neighbour: its pass 5 would find no strip to work on)
+    for (int l = 0; l + 1 < nl; l++) if (int rc = vrt_amr_level_pass(c, s, l, 5, 1)) return rc;
     return vrt_amr_level_pass(c, s, -1, 6, 1);
 }
 
