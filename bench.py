@@ -276,6 +276,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-fields-phase", action="store_true")
+    ap.add_argument("--no-self-check", action="store_true", help="skip the pre-flight fused-vs-split check (profiling runs: keeps its launches out of the capture window)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -311,7 +312,7 @@ def main():
         nx = WORKLOADS["c3"][0] * n_gpus
         wl = f"c3 per GPU ({nx}x{np_})"
 
-    self_check = fused_vs_split_self_check(vb, S, np_, local_rank) if rank == 0 else None
+    self_check = fused_vs_split_self_check(vb, S, np_, local_rank) if (rank == 0 and not args.no_self_check) else None
 
     run = vb.LaserPlasmaRun(nx, np_, density=DENSITY, device=local_rank, slab=(rank, n_gpus) if n_gpus > 1 else None,
                             graph=not args.no_graph)

@@ -118,7 +118,8 @@ int vrt_vlasov_substep(vrt_ctx* ctx, int s, int depth, double dt, int step, int 
 int vrt_push_data(vrt_ctx* ctx, int s, int val);
 int vrt_push_boundary_c(vrt_ctx* ctx, int s);
 /* Level::PushData(updateType, val) (Level.cpp:88-126) on the level of the given depth: 0 UpdateInterriorPoints, 1 UpdateSameLevelBoundaries,
- * 2 UpdateDifferentLevelBoundaries, 3 UpdateCornerPoints, 4 CalculateSameBoundaryC, 5 CalculateDifferentBoundaryC, 6 UpdateSameBoundaryC. */
+ * 2 UpdateDifferentLevelBoundaries, 3 UpdateCornerPoints, 4 CalculateSameBoundaryC, 5 CalculateDifferentBoundaryC, 6 UpdateSameBoundaryC.
+ * depth = -1 serves every level in one launch; valid for the passes that pair patches of one level only (1, 4, 6). */
 int vrt_level_push(vrt_ctx* ctx, int s, int depth, int update_type, int val);
 /* EMFieldSolver::RGKStep(step, dt) (EMSolver.cpp:194-202) = RGKCalculateRHS + RGKUpdateIntermediateSolution +
  * InterpolateToFaces; by0/bz0 are the host-evaluated Settings::GetBY/GetBZ(0, time) (EMSolver.cpp:501-502). */

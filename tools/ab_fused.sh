@@ -8,7 +8,7 @@ for m in ${MASKS:-0x00 0x0f 0x3f}; do
     timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_reference_on_box.py tests/test_gpu_checkpoint.py -q -k "fused or ragged or interior or benchmark_p_grid or hundred or checkpoint or per_step" > gpurun_out/ab_pytest_$m.log 2>&1
     echo "LEAN=$m pytest rc=$? $(tail -1 gpurun_out/ab_pytest_$m.log)"
   fi
-  timeout 300 python bench.py --steps 4 --warmup 3 --no-cpu-baseline --skip-fields-phase > gpurun_out/ab_bench_$m.json 2> gpurun_out/ab_bench_$m.err
+  timeout 300 python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-self-check --skip-fields-phase > gpurun_out/ab_bench_$m.json 2> gpurun_out/ab_bench_$m.err
   python - <<P
 import json
 d=json.load(open("gpurun_out/ab_bench_$m.json"))

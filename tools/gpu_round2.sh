@@ -16,7 +16,7 @@ fi
 # ncu --set full: one launch each of stages 0, 3, 5 (species 0 and 1 alternate; the 4th step is profiled: 3 warm-up steps x 2
 # species x 3 matching stages = 18 launches skipped)
 if [ -z "$SKIP_NCU" ]; then
-timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k 'regex:k_fused_stageILi[035]E' -s 18 -c 6 -o gpurun_out/prof_fused_$TAG -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --skip-fields-phase > gpurun_out/prof_bench_$TAG.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k 'regex:k_fused_stageILi[035]E' -s 18 -c 6 -o gpurun_out/prof_fused_$TAG -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-self-check --skip-fields-phase > gpurun_out/prof_bench_$TAG.log 2>&1
 echo "ncu fused rc=$?"; tail -1 gpurun_out/prof_bench_$TAG.log | cut -c1-160
 python tools/ncu_summary.py gpurun_out/prof_fused_$TAG.ncu-rep > $P/ncu_fused_${KV}_${TAG}_summary.txt
 python tools/ncu_source_summary.py gpurun_out/prof_fused_$TAG.ncu-rep 30 > $P/ncu_fused_${KV}_${TAG}_source.txt 2>/dev/null
@@ -24,8 +24,8 @@ python tools/update_traffic.py $KV profiles/ncu_fused_${KV}_${TAG}_summary.txt g
 OUT=prof_moments_$TAG bash tools/profile_moments.sh > /dev/null
 python tools/ncu_summary.py gpurun_out/prof_moments_$TAG.ncu-rep > $P/ncu_moments_${TAG}_summary.txt
 python tools/ncu_source_summary.py gpurun_out/prof_moments_$TAG.ncu-rep 30 > $P/ncu_moments_${TAG}_source.txt 2>/dev/null
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --skip-fields-phase > gpurun_out/launches_bench_$TAG.log 2>&1
-python tools/launch_summary.py gpurun_out/launches_$TAG.csv "python bench.py --steps 2 --warmup 3 --no-cpu-baseline --skip-fields-phase under ncu --metrics gpu__time_duration.sum ($KV)" > $P/launches_${TAG}_${KV}_summary.txt 2>/dev/null
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-self-check --skip-fields-phase > gpurun_out/launches_bench_$TAG.log 2>&1
+python tools/launch_summary.py gpurun_out/launches_$TAG.csv "python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-self-check --skip-fields-phase under ncu --metrics gpu__time_duration.sum ($KV)" > $P/launches_${TAG}_${KV}_summary.txt 2>/dev/null
 head -8 $P/launches_${TAG}_${KV}_summary.txt
 fi
 # launch list of the 3-level AMR workload through the host classes (what the step is made of)
