@@ -179,7 +179,10 @@ __device__ __forceinline__ double cell_a_sq(const VrtFields& F, int i) {   // EM
     double ay = F.Y[VRT_AY][F.M + i], az = F.Y[VRT_AZ][F.M + i];
     return (ay * ay) + (az * az);
 }
-// grid: (n_x*rtb, patches); block reduces over p
+// grid: (n_x*rtb, patches); block reduces over p.  A cell's sums need u = gamma + p/mc at its four surrounding faces and
+// g = mc ln(u_hi/u_lo) of itself and its two p-neighbours: every thread forms u at ONE face and g of ONE cell and the block shares
+// them through shared memory (the same expressions on the same operands as forming them per cell — four square roots, three
+// divisions and three logarithms per cell before — so the values are the same bits).
 __global__ void __launch_bounds__(128) k_moments(const VrtPatchDev* patches, Sp sp, VrtFields F) { vrt_pdl_sync();
     const VrtPatchDev& P = patches[blockIdx.y];
     const int rtb = P.rtb;
@@ -188,19 +191,26 @@ __global__ void __launch_bounds__(128) k_moments(const VrtPatchDev* patches, Sp 
     const double q = sp.q, c1 = sp.m_inv * VRT_C_INV, c2 = 1 / c1, c3 = 1 / 48.0;
     const double a2 = q * q * cell_a_sq(F, (i + P.x_pos) * rtb + k);
     __shared__ double coef[3 * RTB_TAB];
+    __shared__ double su[128 + 3], sg[128 + 2];       // u at faces j0 - 1 .. j0 + 129, g of cells j0 - 1 .. j0 + 128
     const double* tab = rtb <= RTB_TAB ? coef : nullptr;
-    if (tab && (int)threadIdx.x < rtb) rel_coefficients(threadIdx.x, rtb, coef[threadIdx.x], coef[RTB_TAB + threadIdx.x], coef[2 * RTB_TAB + threadIdx.x]);
-    __syncthreads();
+    const int t = threadIdx.x;
+    if (tab && t < rtb) rel_coefficients(t, rtb, coef[t], coef[RTB_TAB + t], coef[2 * RTB_TAB + t]);
+    auto uface = [&](int j) { const double p = momentum(P, sp, j); return gamma_(sp, p, a2) + c1 * p; };
     double rho = 0.0, cur = 0.0;
-    for (int j = threadIdx.x; j < P.n_p; j += blockDim.x) {
-        if (P.flags[NS(P, i, j)] & VRT_NESTED) continue;   // cells covered by a finer patch (Rectangle.cpp:207-208)
-        double t0 = rel_value(P, i, j, k, tab), tm1 = rel_value(P, i, j - 1, k, tab), tp1 = rel_value(P, i, j + 1, k, tab);
-        double pm1 = momentum(P, sp, j - 1), p0 = momentum(P, sp, j), p1 = momentum(P, sp, j + 1), p2 = momentum(P, sp, j + 2);
-        double um1 = gamma_(sp, pm1, a2) + c1 * pm1, u0 = gamma_(sp, p0, a2) + c1 * p0;
-        double u1 = gamma_(sp, p1, a2) + c1 * p1, u2 = gamma_(sp, p2, a2) + c1 * p2;
-        double gm = c2 * log(u1 / u0), gm1 = c2 * log(u0 / um1), gp1 = c2 * log(u2 / u1);
-        rho += t0;
-        cur += t0 * gm + c3 * (gp1 - gm1) * (tp1 - tm1);
+    for (int j0 = 0; j0 < P.n_p; j0 += 128) {
+        __syncthreads();                                // the previous tile's su / sg are no longer read (first pass: coef is written)
+        su[t + 1] = uface(j0 + t);
+        if (t < 3) su[t == 0 ? 0 : 128 + t] = uface(t == 0 ? j0 - 1 : j0 + 127 + t);      // faces j0 - 1, j0 + 128, j0 + 129
+        __syncthreads();
+        sg[t + 1] = c2 * log(su[t + 2] / su[t + 1]);                                       // cell j0 + t: faces j0 + t, j0 + t + 1
+        if (t < 2) { const int e = t == 0 ? 0 : 129; sg[e] = c2 * log(su[e + 1] / su[e]); }   // cells j0 - 1 and j0 + 128
+        __syncthreads();
+        const int j = j0 + t;
+        if (j < P.n_p && !(P.flags[NS(P, i, j)] & VRT_NESTED)) {   // cells covered by a finer patch are skipped (Rectangle.cpp:207-208)
+            const double t0 = rel_value(P, i, j, k, tab), tm1 = rel_value(P, i, j - 1, k, tab), tp1 = rel_value(P, i, j + 1, k, tab);
+            rho += t0;
+            cur += t0 * sg[t + 1] + c3 * (sg[t + 2] - sg[t]) * (tp1 - tm1);
+        }
     }
     __shared__ double sh[2][4];
     for (int o = 16; o > 0; o >>= 1) { rho += __shfl_down_sync(0xffffffffu, rho, o); cur += __shfl_down_sync(0xffffffffu, cur, o); }
