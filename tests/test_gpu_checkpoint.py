@@ -128,3 +128,55 @@ def test_restart_through_the_host_classes(tmp_path):
             compared += 1
     assert "step4/time" not in b and compared > 100
     print(f"restart through the host classes: {compared} records of steps 5..8 bitwise equal")
+
+
+def test_checkpoint_read_is_transactional(tmp_path):
+    """vrt_checkpoint_read validates the whole file before it touches the context: a truncated file, trailing garbage, a corrupt
+    patch count and a checkpoint of another grid are all refused with an error code, nothing throws across the C boundary, and the
+    context keeps its state bit for bit (it continues exactly like an undisturbed twin); a good file still restores afterwards."""
+    import struct
+    good = tmp_path / "good.ckpt"
+    kw = dict(density=0.3)
+
+    def fresh():
+        run = vb.LaserPlasmaRun(128, 64, **kw)
+        run.init_device()
+        run.time = 3 * run.T
+        run.advance(run.calculate_dt())
+        return run
+
+    run, twin = fresh(), fresh()
+    run.ctx.checkpoint_write(good)
+    raw = open(good, "rb").read()
+    header = 8 + 10 * 4 + 2 * 8          # magic, ten ints, dx, time
+    fields = (6 * 8 * run.ctx.M + (run.ctx.N + 1) + 2 * run.ctx.N + 1) * 8
+    n_off = header + fields + 4 * 8 + 4  # species record: VrtSpecies (4 doubles), path, then the patch count
+    bad = {
+        "truncated": raw[: len(raw) // 2],
+        "trailing": raw + b"\0" * 24,
+        "patch_count": raw[:n_off] + struct.pack("<i", 2 ** 30) + raw[n_off + 4:],
+        "zero_patches": raw[:n_off] + struct.pack("<i", 0) + raw[n_off + 4:],
+        "not_a_checkpoint": b"VRTCKPT0" + raw[8:],
+    }
+    other = vb.LaserPlasmaRun(64, 64, **kw)
+    other.init_device()
+    other.ctx.checkpoint_write(tmp_path / "other_grid.ckpt")
+    other.ctx.close()
+    for name, blob in bad.items():
+        p = tmp_path / f"{name}.ckpt"
+        open(p, "wb").write(blob)
+        with pytest.raises(vb.VrtError):
+            run.ctx.checkpoint_read(p)
+    with pytest.raises(vb.VrtError):
+        run.ctx.checkpoint_read(tmp_path / "other_grid.ckpt")
+    # the refused reads left the context untouched: it continues like its twin
+    for r in (run, twin):
+        for _ in range(2):
+            r.advance(r.calculate_dt())
+    for x, y in zip(snapshot(run.ctx, [1, 1]), snapshot(twin.ctx, [1, 1])):
+        assert np.array_equal(x, y)
+    twin.ctx.close()
+    run.ctx.checkpoint_read(good)
+    run.time = run.ctx.get_scalar(S.TIME)
+    run.advance(run.calculate_dt())
+    run.ctx.close()
