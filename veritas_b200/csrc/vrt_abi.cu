@@ -44,6 +44,7 @@ void free_species(VrtSpeciesState& S) {
     S.allocations.clear();
     if (S.d_patches) { cudaFree(S.d_patches); S.d_patches = nullptr; }
     if (S.conn_pool) { cudaFree(S.conn_pool); S.conn_pool = nullptr; }
+    S.d_lb = nullptr; S.lb_first.clear(); S.lb_count.clear();
     S.has_amr = false;
     S.patches.clear(); S.level_patches.clear(); S.desc.clear();
     S.configured = false;
@@ -364,6 +365,7 @@ int vrt_regrid(vrt_ctx* c, int s, int n_patches, const vrt_patch_desc* d) {
         old.allocations.swap(S.allocations); old.patches.swap(S.patches); old.table.swap(S.table); old.table_index.swap(S.table_index);
         old.table_order.swap(S.table_order); old.level_patches.swap(S.level_patches); old.desc.swap(S.desc);
         std::swap(old.d_patches, S.d_patches); std::swap(old.conn_pool, S.conn_pool); std::swap(old.has_amr, S.has_amr);
+        std::swap(old.d_lb, S.d_lb); old.lb_first.swap(S.lb_first); old.lb_count.swap(S.lb_count);
     };
     exchange();
     int rc;

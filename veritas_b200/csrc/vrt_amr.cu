@@ -21,6 +21,7 @@
 // in the reference's order.
 #include "vrt_internal.cuh"
 #include "vrt_launch.cuh"
+#include <cstring>
 #include "vrt_device.cuh"
 #include <algorithm>
 #include <cmath>
@@ -472,6 +473,39 @@ __global__ void k_level_boundary_fluxes(const VrtPatchDev* level, const VrtPatch
     }
 }
 
+// The same over the list of flagged faces (refinement ratio 2): one thread per (face, flux kind, fine sub-face), so that a warp is
+// 32 lanes of equal work instead of the one or two flagged cells a warp of the scan above holds; the two fine-face fluxes of a coarse
+// face meet by shuffle and are added in the reference's order  t = 0 + F(k = 0) + F(k = 1), t *= 1/r^2  (Rectangle.hpp:132-178).
+__global__ void k_lb_fluxes_r2(const VrtLbFace* faces, int n, const VrtPatchDev* all, int step, Sp sp, VrtFields F) { vrt_pdl_sync();
+    constexpr int r = 2;
+    const int kinds = step == 0 ? 2 : 1;              // high-order always, low-order at stage 0 only (quirk Q1)
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int e = t / (kinds * r), rem = t % (kinds * r), low = rem / r, k = rem % r;
+    const bool valid = e < n;
+    double val = 0.0;
+    int dir = 0; long c = 0; int patch = 0;
+    if (valid) {
+        const VrtLbFace f = faces[e];
+        patch = f.patch; dir = f.dir; c = f.cell;
+        const VrtPatchDev& P = all[patch];
+        const int i = (int)(c / P.pitch) - 2, j = (int)(c % P.pitch) - 2;
+        const int finer = dir == 0 ? P.finer_x[c] : P.finer_p[c];
+        const VrtPatchDev& Q = all[finer];
+        const int ii = (P.x_pos + i) * r - Q.x_pos, jj = (P.p_pos + j) * r - Q.p_pos;
+        const int kind = dir + 2 * low;               // 0 X, 1 P, 2 XL, 3 PL
+        val = dir == 0 ? rgk_flux(all, finer, ii, jj + k, kind, r, sp, F) : rgk_flux(all, finer, ii + k, jj, kind, r, sp, F);
+    }
+    const double other = __shfl_down_sync(0xffffffffu, val, 1);      // lane k = 0 receives the k = 1 flux of the same face and kind
+    if (valid && k == 0) {
+        double tsum = 0.0;
+        tsum += val; tsum += other;
+        tsum *= (1.0 / (double)(r * r));
+        const VrtPatchDev& P = all[patch];
+        if (dir == 0) { if (low) P.FxL[c] = tsum; else P.FxH[step * P.npad + c] = tsum; }
+        else { if (low) P.FpL[c] = tsum; else P.FpH[step * P.npad + c] = tsum; }
+    }
+}
+
 // ---- K6b: limiter sync, one thread per side strip ------------------------------------------------------------------------
 // pass 4: CalculateSameBoundaryC -> SetCFromSameLevel (Rectangle.cpp:1835-1877, 1795-1833)
 // pass 5: CalculateDifferentBoundaryC -> SetCFromDifferentLevel (1706-1763, 1625-1704)
@@ -562,10 +596,35 @@ int vrt_amr_upload_connectivity(vrt_ctx* c, int s, const vrt_conn& C) {
         size_t chars = 2 * (size_t)p.ns_x + 2 * (size_t)p.ns_p + p.flags.size();
         bytes += ints * sizeof(int) + ((chars + 15) / 16) * 16;
     }
+    // the flagged coarse faces (index ranges of Rectangle.cpp:1313-1394: x-faces i in [0, n_x], j in [-1, n_p]; p-faces i in [-1, n_x],
+    // j in [0, n_p]), in table order, hence grouped by depth
+    std::vector<VrtLbFace> lb;
+    S.lb_first.assign(S.level_patches.size(), 0); S.lb_count.assign(S.level_patches.size(), 0);
+    for (int ti = 0; ti < n; ti++) {
+        const VrtConnPatch& p = C.P[S.table_order[ti]];
+        const VrtPatchDev& T = S.table[ti];
+        const size_t before = lb.size();
+        for (long cidx = 0; cidx < T.npad; cidx++) {
+            const unsigned char fl = p.flags[cidx];
+            if (!(fl & (VRT_LBX | VRT_LBP))) continue;
+            const int i = (int)(cidx / T.pitch) - 2, j = (int)(cidx % T.pitch) - 2;
+            if ((fl & VRT_LBX) && i >= 0 && i <= T.n_x && j >= -1 && j <= T.n_p) lb.push_back(VrtLbFace{ti, 0, cidx});
+            if ((fl & VRT_LBP) && i >= -1 && i <= T.n_x && j >= 0 && j <= T.n_p) lb.push_back(VrtLbFace{ti, 1, cidx});
+        }
+        if (lb.size() > before) {
+            if (S.lb_count[T.depth] == 0) S.lb_first[T.depth] = (int)before;
+            S.lb_count[T.depth] += (int)(lb.size() - before);
+        }
+    }
+    bytes = (bytes + 15) & ~(size_t)15;
+    const size_t lb_off = bytes;
+    bytes += lb.size() * sizeof(VrtLbFace);
     std::vector<unsigned char> host(bytes, 0);
+    if (!lb.empty()) std::memcpy(host.data() + lb_off, lb.data(), lb.size() * sizeof(VrtLbFace));
     if (S.conn_pool) { cudaFree(S.conn_pool); S.conn_pool = nullptr; }
     VRT_CUDA(c, cudaMalloc(&S.conn_pool, std::max<size_t>(bytes, 16)));
     unsigned char* dbase = (unsigned char*)S.conn_pool;
+    S.d_lb = lb.empty() ? nullptr : (VrtLbFace*)(dbase + lb_off);
     S.has_amr = false;
     for (int ti = 0; ti < n; ti++) {
         const VrtConnPatch& p = C.P[S.table_order[ti]];
@@ -670,9 +729,20 @@ int vrt_amr_push_boundary_c(vrt_ctx* c, int s) {
     return vrt_amr_level_pass(c, s, -1, 6, 1);
 }
 
+static int launch_lb_list(vrt_ctx* c, VrtSpeciesState& S, int first, int count, int step) {
+    const int kinds = step == 0 ? 2 : 1;
+    const long threads = (long)count * kinds * 2;
+    vrt_launch(k_lb_fluxes_r2, dim3(blocks(threads, 128)), dim3(128), c->stream, (const VrtLbFace*)(S.d_lb + first), count, (const VrtPatchDev*)S.d_patches, step,
+               make_sp(S.sp), c->F);
+    c->launches += 1;
+    VRT_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
 int vrt_amr_level_boundary_fluxes(vrt_ctx* c, int s, int depth, int step) {
     VrtSpeciesState& S = c->S[s];
     if (depth == 0 || S.level_patches[depth].empty() || S.level_patches[depth - 1].empty()) return 0;
+    if (c->refinement_ratio == 2 && S.d_lb) return S.lb_count[depth] ? launch_lb_list(c, S, S.lb_first[depth], S.lb_count[depth], step) : 0;
     long m = 0;
     for (int p : S.level_patches[depth]) m = std::max(m, S.table[p].npad);
     vrt_launch(k_level_boundary_fluxes, dim3(dim3(blocks(m, 128), (unsigned)S.level_patches[depth].size())), dim3(128), c->stream, 
@@ -691,6 +761,11 @@ int vrt_amr_level_boundary_fluxes_all(vrt_ctx* c, int s, int step) {
     for (size_t d = 1; d < S.level_patches.size(); d++)
         for (int p : S.level_patches[d]) { if (first < 0) first = p; m = std::max(m, S.table[p].npad); }
     if (first < 0 || !S.has_amr) return 0;
+    if (c->refinement_ratio == 2 && S.d_lb) {
+        int lo = -1, cnt = 0;
+        for (size_t d = 1; d < S.lb_count.size(); d++) if (S.lb_count[d]) { if (lo < 0) lo = S.lb_first[d]; cnt += S.lb_count[d]; }
+        return cnt ? launch_lb_list(c, S, lo, cnt, step) : 0;
+    }
     vrt_launch(k_level_boundary_fluxes, dim3(dim3(blocks(m, 128), (unsigned)(S.table.size() - first))), dim3(128), c->stream, 
         S.d_patches + first, S.d_patches, step, c->refinement_ratio, make_sp(S.sp), c->F);
     c->launches += 1;

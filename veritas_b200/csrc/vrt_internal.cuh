@@ -79,6 +79,9 @@ struct VrtPatchDev {
     unsigned char* flags;             // VRT_NESTED | VRT_LBX | VRT_LBP per padded cell
 };
 enum { VRT_NESTED = 1, VRT_LBX = 2, VRT_LBP = 4 };
+// one coarse face whose flux is replaced by the finer patch's (is_interrior_level_boundary_{x,p}): table index of the coarse patch,
+// direction (0: x-face, 1: p-face), padded cell index — the list lets the flux-matching kernel launch exactly the work there is
+struct VrtLbFace { int patch; int dir; long cell; };
 
 // Host-side connectivity tables of one species' hierarchy (caller's patch numbering unless noted)
 struct VrtConnPatch {
@@ -130,6 +133,8 @@ struct VrtSpeciesState {
     std::vector<double*> allocations;
     VrtSlabMaps maps;
     void* conn_pool = nullptr;           // device pool holding the connectivity tables of all patches
+    VrtLbFace* d_lb = nullptr;           // (inside conn_pool) the flagged coarse faces of all levels, grouped by depth like the table
+    std::vector<int> lb_first, lb_count; // per depth: range in d_lb
     bool has_amr = false;                // any nested cell / coarse-fine face / same-level neighbour
     std::vector<std::vector<int>> level_patches;   // table indices per depth (contiguous ranges)
     // fused path
