@@ -312,6 +312,39 @@ __global__ void __launch_bounds__(PTHR) k_poisson_small(VrtFields F, double* par
     if (threadIdx.x == 0) { F.Ex0[1] = ex0_new; F.Ex0[0] = ex0_new; }
 }
 
+// The same solve with the tiles side by side: one thread-block cluster of up to PSMALL CTAs, one tile each, the hardware cluster barrier
+// (release / acquire at cluster scope, so the global scratch one CTA wrote is visible to the others) where the multi-CTA version has
+// kernel boundaries.  The passes run in parallel over the tiles instead of one after the other in a single CTA: the latency of five
+// passes, not of five passes times the tile count, on the critical path of every RK stage of a short-grid step.  Same device
+// functions, same tile index, same partial sums: same bits.
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__global__ void __launch_bounds__(PTHR) k_poisson_cluster(VrtFields F, double* part, int G) {
+    vrt_pdl_sync();
+    const int blk = blockIdx.x, nc = gridDim.x;            // nc = cluster size (>= G, a power of two); CTAs beyond G only keep the barriers
+    const bool work = blk < G;
+    if (work) d_poisson_rhs(F, part, blk);
+    cluster_sync_all();
+    if (work) d_poisson_conv(F, part, part + PMAXT, G, blk);
+    cluster_sync_all();
+    if (work) d_poisson_scan1(F, part + PMAXT, part + 2 * PMAXT, G, blk);
+    cluster_sync_all();
+    if (work) d_poisson_dsum(F, part + 2 * PMAXT, part + 3 * PMAXT, G, blk);
+    cluster_sync_all();
+    if (work) d_poisson_scan2(F, part + 2 * PMAXT, part + 3 * PMAXT, G, blk);
+    cluster_sync_all();
+    __shared__ double ex0_new;
+    if (threadIdx.x == 0) {
+        const double ex0 = *F.Ex0;
+        ex0_new = ex0 + -((efield_base(F, -1) + ex0) + (efield_base(F, 0) + ex0)) * 0.5;
+    }
+    __syncthreads();
+    for (int i = blk * PTHR + (int)threadIdx.x - F.epad; i < F.N + F.epad; i += nc * PTHR) F.E[i + F.epad] = efield_base(F, i) + ex0_new;
+    cluster_sync_all();                                     // every CTA has read the old Ex0
+    if (blk == 0 && threadIdx.x == 0) { F.Ex0[1] = ex0_new; F.Ex0[0] = ex0_new; }
+}
+
 // ---- EstimateCFLBound (EMSolver.cpp:631-664), un-offset indexing kept (quirk Q3) ---------------------
 struct CflSpecies { int n; double m[8], q[8], dps[8]; double dpsMax; };
 __global__ void k_cfl(VrtFields F, CflSpecies sp) {
@@ -412,8 +445,17 @@ int vrt_fields_poisson(vrt_ctx* c) {
     const int G = (F.N + PTILE - 1) / PTILE;
     if (G > PMAXT) { c->err = "vrt_poisson: x_size_finest too large for the tiled solver"; return VRT_ERR_ARG; }
     double* part = F.scratch + 3L * F.N + 8;      // 4 arrays of PMAXT tile partials behind the three N-vectors and sum(b)
-    const bool small_ok = !(getenv("VRT_POISSON_SMALL") && atoi(getenv("VRT_POISSON_SMALL")) == 0);     // 0: the multi-CTA passes (tests)
-    if (G <= PSMALL && small_ok) {
+    // short grids: VRT_POISSON_SMALL = 2 (default) one cluster launch, 1 one single-CTA launch, 0 the multi-kernel passes (tests)
+    const int small_mode = getenv("VRT_POISSON_SMALL") ? atoi(getenv("VRT_POISSON_SMALL")) : 2;
+    if (G <= PSMALL && small_mode == 2) {
+        unsigned nc = 1;
+        while ((int)nc < G) nc <<= 1;
+        vrt_launch_cluster(k_poisson_cluster, dim3(nc), dim3(PTHR), nc, c->stream, F, part, G);
+        c->launches += 1;
+        VRT_CUDA(c, cudaGetLastError());
+        return 0;
+    }
+    if (G <= PSMALL && small_mode == 1) {
         const size_t smem = sizeof(double) * (3 * (size_t)F.N + 8 + 32);
         static bool attr_dev[64] = {};
         bool& attr = attr_dev[c->device & 63];

@@ -29,6 +29,19 @@ inline cudaError_t vrt_launch_smem(void (*kernel)(KArgs...), dim3 grid, dim3 blo
     cfg.attrs = attr; cfg.numAttrs = vrt_pdl_enabled() ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
 }
+// the same for a kernel whose CTAs form one thread-block cluster of `cluster_x` CTAs (hardware cluster barrier between its phases)
+template <typename... KArgs, typename... Args>
+inline cudaError_t vrt_launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, unsigned cluster_x, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster_x; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = vrt_pdl_enabled() ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
 template <typename... KArgs, typename... Args>
 inline cudaError_t vrt_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args&&... args) {
     return vrt_launch_smem(kernel, grid, block, 0, stream, std::forward<Args>(args)...);
