@@ -180,3 +180,37 @@ def test_checkpoint_read_is_transactional(tmp_path):
     run.time = run.ctx.get_scalar(S.TIME)
     run.advance(run.calculate_dt())
     run.ctx.close()
+
+
+def test_failed_set_hierarchy_leaves_no_half_built_species():
+    """A refused or failed vrt_set_hierarchy / vrt_regrid must not leave a species with descriptors but no storage: every later
+    hot-path call answers with an error code (VRT_ERR_STATE) instead of touching freed planes, and a valid hierarchy can be set
+    afterwards."""
+    d = load_golden("amr3_48x32_regrid")
+    mt = meta(d)
+    ctx = new_ctx(d, mt)
+    H = hierarchy_from_dump(d, "step2")
+    keys = set_hierarchy(ctx, H)
+    ctx.load_reference_state(d, "step2", keys)
+    ctx.moments()
+    # (1) a descriptor vrt_set_hierarchy refuses (odd size on a refined level): the species holds nothing afterwards
+    bad = [dict(p) for p in H[0]]
+    bad[0]["n_x"] += 1
+    with pytest.raises(vb.VrtError):
+        ctx.set_hierarchy(0, bad)
+    for call in (ctx.moments, lambda: ctx.push_data(0, 1), lambda: ctx.download_f(0, 0, 1), lambda: ctx.step(1e-18, [0.0] * 12)):
+        with pytest.raises(vb.VrtError):
+            call()
+    # (2) a valid hierarchy afterwards: the context works again
+    ctx.set_hierarchy(0, H[0])
+    ctx.load_reference_state(d, "step2", keys)
+    ctx.moments()
+    # (3) a refused vrt_regrid keeps the resident hierarchy and its data
+    before = [ctx.download_f(0, k, 1) for k in range(len(H[0]))]
+    with pytest.raises(vb.VrtError):
+        ctx.regrid(0, bad)
+    ctx.patches[0] = [{k: p[k] for k in S.DESC_KEYS} for p in H[0]]      # the harness's own copy of the descriptors
+    for k, a in enumerate(before):
+        assert np.array_equal(ctx.download_f(0, k, 1), a)
+    ctx.moments()
+    ctx.close()
