@@ -50,8 +50,15 @@ void free_species(VrtSpeciesState& S) {
     S.configured = false;
 }
 
-void drop_graphs(vrt_ctx* c) {
-    for (int k = 0; k < 3; k++) if (c->graph_step3[k]) { cudaGraphExecDestroy(c->graph_step3[k]); c->graph_step3[k] = nullptr; }
+// keep_for_update: the step executables are parked in graph_stale (see vrt_internal.cuh) instead of being destroyed
+void drop_graphs(vrt_ctx* c, bool keep_for_update = false) {
+    for (int k = 0; k < 3; k++) {
+        if (!c->graph_step3[k]) continue;
+        if (keep_for_update && !c->graph_stale[k]) c->graph_stale[k] = c->graph_step3[k];
+        else cudaGraphExecDestroy(c->graph_step3[k]);
+        c->graph_step3[k] = nullptr;
+    }
+    if (!keep_for_update) for (int k = 0; k < 3; k++) if (c->graph_stale[k]) { cudaGraphExecDestroy(c->graph_stale[k]); c->graph_stale[k] = nullptr; }
     if (c->graph_fields) { cudaGraphExecDestroy(c->graph_fields); c->graph_fields = nullptr; }
 }
 
@@ -358,7 +365,7 @@ int vrt_regrid(vrt_ctx* c, int s, int n_patches, const vrt_patch_desc* d) {
     }
     cudaSetDevice(c->device);
     VRT_CUDA(c, cudaStreamSynchronize(c->stream));
-    drop_graphs(c);
+    drop_graphs(c, true);
     // park the old storage; it comes back unchanged if the new hierarchy cannot be built or filled
     VrtSpeciesState old;
     auto exchange = [&]() {
@@ -860,9 +867,18 @@ int vrt_step(vrt_ctx* c, double dt, const double laser[12]) {
             for (size_t s = 0; s < c->S.size(); s++) { c->graph_end_state[key][s] = {c->S[s].i_f0, c->S[s].i_f1}; c->S[s].i_f0 = saved[s].first; c->S[s].i_f1 = saved[s].second; }
             if (r) { if (g) cudaGraphDestroy(g); return r; }
             if (e != cudaSuccess) { c->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e); return VRT_ERR_CUDA; }
-            e = cudaGraphInstantiate(&c->graph_step3[key], g, 0);
+            if (c->graph_stale[key]) {       // after a regrid: same topology -> update the parked executable in place (VRT_GRAPH_UPDATE=0: A/B switch)
+                static const bool update_on = !(getenv("VRT_GRAPH_UPDATE") && atoi(getenv("VRT_GRAPH_UPDATE")) == 0);
+                cudaGraphExecUpdateResultInfo info;
+                if (update_on && cudaGraphExecUpdate(c->graph_stale[key], g, &info) == cudaSuccess) c->graph_step3[key] = c->graph_stale[key];
+                else { cudaGetLastError(); cudaGraphExecDestroy(c->graph_stale[key]); }
+                c->graph_stale[key] = nullptr;
+            }
+            if (!c->graph_step3[key]) {
+                e = cudaGraphInstantiate(&c->graph_step3[key], g, 0);
+                if (e != cudaSuccess) { cudaGraphDestroy(g); c->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e); return VRT_ERR_CUDA; }
+            }
             cudaGraphDestroy(g);
-            if (e != cudaSuccess) { c->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e); return VRT_ERR_CUDA; }
         }
         VRT_CUDA(c, cudaGraphLaunch(c->graph_step3[key], c->stream));
         for (size_t s = 0; s < c->S.size(); s++) { c->S[s].i_f0 = c->graph_end_state[key][s].first; c->S[s].i_f1 = c->graph_end_state[key][s].second; }

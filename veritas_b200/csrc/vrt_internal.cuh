@@ -169,6 +169,10 @@ struct vrt_ctx {
     // step graph
     VrtStepParams* d_params = nullptr; VrtStepParams* h_params = nullptr;
     cudaGraphExec_t graph_step3[3] = {nullptr, nullptr, nullptr};   // keyed by the plane-rotation state at step start
+    // executables of the step graph a regrid invalidated: the re-captured graph has the same topology as long as the same levels are
+    // populated, so the old executable is UPDATED with the new nodes' parameters (cudaGraphExecUpdate) instead of instantiating a new
+    // one — instantiation is the larger part of what a regrid costs a small hierarchy
+    cudaGraphExec_t graph_stale[3] = {nullptr, nullptr, nullptr};
     cudaGraphExec_t graph_fields = nullptr;
     long graph_launches[3] = {0, 0, 0}, graph_fields_launches = 0;
     std::pair<int, int> graph_end_state[3][8];
