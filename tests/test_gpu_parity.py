@@ -171,13 +171,13 @@ def test_poisson_against_dense_lu_oracle():
 
 
 def test_poisson_single_cta_equals_tiled_passes(monkeypatch):
-    """Short x grids (N <= 4096) run UpdatePotential + the E table as one launch — a thread-block cluster with one tile per CTA
-    (default) or a single CTA walking the tiles; both must produce the bits of the five multi-kernel passes (same per-tile
+    """Short x grids (N <= 4096) run UpdatePotential + the E table as one launch — a thread-block cluster with one tile per CTA,
+    one wide CTA with a thread group per tile, or a single block walking the tiles; all must produce the bits of the five multi-kernel passes (same per-tile
     arithmetic, same fixed-order sums of tile partials), ragged last tile and a three-tile grid included."""
     rng = np.random.default_rng(3)
     for N in (40, 1024, 2048, 3000, 4096):
         out = {}
-        for small in ("2", "1", "0"):
+        for small in ("3", "2", "1", "0"):
             monkeypatch.setenv("VRT_POISSON_SMALL", small)
             ctx = vb.Context(1)
             ctx.set_grid(N, 1e-5 / N, 2, 2, 2, 0)
@@ -189,7 +189,7 @@ def test_poisson_single_cta_equals_tiled_passes(monkeypatch):
             ctx.poisson(); ctx.poisson()          # twice: the incremental Ex0 update (quirk Q4) goes through both paths
             out[small] = (ctx.get_1d(S.PHI), ctx.get_1d(S.EFIELD), ctx.get_scalar(S.EX0))
             ctx.close()
-        for mode in ("2", "1"):
+        for mode in ("3", "2", "1"):
             assert np.array_equal(out[mode][0], out["0"][0]) and np.array_equal(out[mode][1], out["0"][1]) and out[mode][2] == out["0"][2], (N, mode)
 
 

@@ -96,34 +96,64 @@ __global__ void k_field_faces(VrtFields F) { vrt_pdl_sync();
 // so 17 terms per side are exact to fp64.  D y = z with y_0 = 0 is two running sums.  O(N), no N x N matrix.
 constexpr int PK = 17;
 
-__device__ double block_sum(double v, double* sh) {
-    __syncthreads();
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        double t = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
-        if (threadIdx.x == 0) sh[32] = t;
+// The passes below are written for a "block" of PTHR threads working on tile `blk`.  WIDE = false: the block is the CTA (multi-CTA
+// passes, the cluster kernel, the single-CTA kernel walking the tiles).  WIDE = true: the block is one of up to PSMALL groups of PTHR
+// consecutive threads of a wide CTA, each on its own tile, synchronising among themselves with a named barrier and keeping their
+// own copy of every shared work array — the same arithmetic per thread, warp and group, so the same bits.
+constexpr int PTHR = 256, PEL = 4, PTILE = PTHR * PEL;
+constexpr int PMAXT = 4096;      // tiles: N <= 4 Mi finest cells
+constexpr int PSMALL = 4;        // tiles of a "short" grid (N <= 4096: BASELINE configs 1, 2, 4)
+__host__ __device__ constexpr int psw(int e) { return e + (e >> 2); }                // padded position (see Blk::at)
+__host__ __device__ constexpr int psw_len(int n) { return (psw(n) + 2) & ~1; }        // padded length of n entries, even
+constexpr int PTILE_SW = psw_len(PTILE + 2 * 17);                                    // the convolution's staged tile (PK = 17), padded
+template <bool WIDE> struct Blk {
+    static constexpr int groups = WIDE ? PSMALL : 1;
+    __device__ static __forceinline__ int tid() { return WIDE ? (int)(threadIdx.x & (PTHR - 1)) : (int)threadIdx.x; }
+    __device__ static __forceinline__ int grp() { return WIDE ? (int)(threadIdx.x / PTHR) : 0; }
+    __device__ static __forceinline__ void sync() {
+        if (WIDE) asm volatile("bar.sync %0, %1;" ::"r"(grp() + 1), "n"(PTHR) : "memory");
+        else __syncthreads();
     }
-    __syncthreads();
+    // Position of entry i of an N-vector of the scratch.  A thread owns PEL = 4 consecutive entries, so in shared memory (WIDE) a
+    // half-warp's 8-byte accesses to "entry k of my run" would be 32 bytes apart — four to a bank.  One pad entry after every four
+    // (i + i/4: 40 bytes apart, 5 coprime to 16) spreads them over all banks.  Global scratch (WIDE = false) stays dense.
+    __device__ static __forceinline__ int at(int i) { return WIDE ? i + (i >> 2) : i; }
+    __device__ static __forceinline__ int stride(int N) { return WIDE ? psw_len(N) : N; }
+};
+
+template <bool WIDE>
+__device__ double block_sum(double v, double* sh) {
+    using B = Blk<WIDE>;
+    const int tid = B::tid();
+    B::sync();
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((tid & 31) == 0) sh[tid >> 5] = v;
+    B::sync();
+    if (tid < 32) {
+        double t = tid < (PTHR >> 5) ? sh[tid] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+        if (tid == 0) sh[32] = t;
+    }
+    B::sync();
     return sh[32];
 }
 // exclusive prefix over the per-thread totals of a block; returns the offset for this thread
+template <bool WIDE>
 __device__ double block_excl_scan(double v, double* sh, double* total) {
-    __syncthreads();
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    using B = Blk<WIDE>;
+    B::sync();
+    const int lane = B::tid() & 31, w = B::tid() >> 5;
     double inc = v;
     for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
     if (lane == 31) sh[w] = inc;
-    __syncthreads();
+    B::sync();
     if (w == 0) {
-        double t = lane < (blockDim.x >> 5) ? sh[lane] : 0.0, ti = t;
+        double t = lane < (PTHR >> 5) ? sh[lane] : 0.0, ti = t;
         for (int o = 1; o < 32; o <<= 1) { double u = __shfl_up_sync(0xffffffffu, ti, o); if (lane >= o) ti += u; }
         sh[lane] = ti - t;               // exclusive warp offsets
         if (lane == 31) sh[32] = ti;     // block total
     }
-    __syncthreads();
+    B::sync();
     *total = sh[32];
     return sh[w] + (inc - v);
 }
@@ -136,42 +166,49 @@ __device__ double block_excl_scan(double v, double* sh, double* total) {
 //   k_poisson_scan1 c = inclusive prefix of z, tile sums
 //   k_poisson_dsum  tile sums of d = mean(c) - c
 //   k_poisson_scan2 PHI_0 = sum(b), PHI_i = sum_{k<i} d_k
-constexpr int PTHR = 256, PEL = 4, PTILE = PTHR * PEL;
-constexpr int PMAXT = 4096;      // tiles: N <= 4 Mi finest cells
 
-// sum of part[0..G) (returned to all threads) and, for this CTA, of part[0..blk): thread t owns a contiguous run of partials
+// sum of part[0..G) (returned to all threads) and, for this block, of part[0..blk): thread t owns a contiguous run of partials
+template <bool WIDE>
 __device__ double partial_prefix(const double* part, int G, int blk, double* sh, double* total) {
-    __shared__ double own;
-    const int cp = (G + PTHR - 1) / PTHR, lo = threadIdx.x * cp, hi = min(G, lo + cp);
+    using B = Blk<WIDE>;
+    __shared__ double own[B::groups];
+    const int cp = (G + PTHR - 1) / PTHR, lo = B::tid() * cp, hi = min(G, lo + cp);
     double loc = 0.0, before = 0.0;
     for (int k = lo; k < hi; k++) { if (k == blk) before = loc; loc += part[k]; }
-    const double off = block_excl_scan(loc, sh, total);
-    if (blk >= lo && blk < hi) own = off + before;
-    __syncthreads();
-    return own;
+    const double off = block_excl_scan<WIDE>(loc, sh, total);
+    if (blk >= lo && blk < hi) own[B::grp()] = off + before;
+    B::sync();
+    return own[B::grp()];
 }
 
+template <bool WIDE>
 __device__ __forceinline__ void d_poisson_rhs(VrtFields F, double* part, const int blk) {
-    __shared__ double sh[40];
-    const int N = F.N, i0 = blk * PTILE + threadIdx.x * PEL;
+    using B = Blk<WIDE>;
+    __shared__ double sh_[B::groups][40];
+    double* sh = sh_[B::grp()];
+    const int N = F.N, i0 = blk * PTILE + B::tid() * PEL, p0 = B::at(i0);      // i0 is a multiple of 4: entry i0 + k sits at p0 + k
     const double te = VRT_EPS0_INV, w = F.dx * F.dx;
     double s = 0.0;
 #pragma unroll
     for (int k = 0; k < PEL; k++) {
         const int i = i0 + k;
-        if (i < N) { double v = te * (F.charge[i] + F.neutral[i]); v *= w; F.scratch[i] = v; s += v; }
+        if (i < N) { double v = te * (F.charge[i] + F.neutral[i]); v *= w; F.scratch[p0 + k] = v; s += v; }
     }
-    const double t = block_sum(s, sh);
-    if (threadIdx.x == 0) part[blk] = t;
+    const double t = block_sum<WIDE>(s, sh);
+    if (B::tid() == 0) part[blk] = t;
 }
 
-__device__ __forceinline__ void d_poisson_conv(VrtFields F, const double* part_b, double* part_z, int G, const int blk) {
-    __shared__ double sh[40];
-    __shared__ double green[PK + 1];
-    __shared__ double tile[PTILE + 2 * PK];
-    const int N = F.N, tid = threadIdx.x, t0 = blk * PTILE;
+template <bool WIDE>
+__device__ __forceinline__ void d_poisson_conv(VrtFields F, const double* part_b, double* part_z, int G, const int blk, double* tiles = nullptr) {
+    using B = Blk<WIDE>;
+    static_assert(PTILE_SW == psw_len(PTILE + 2 * PK), "PTILE_SW");
+    __shared__ double sh_[B::groups][40];
+    __shared__ double green_[B::groups][PK + 1];
+    __shared__ double tile_[WIDE ? 2 : PTILE_SW];                  // WIDE: the groups' tiles live in the dynamic allocation (`tiles`)
+    double* sh = sh_[B::grp()]; double* green = green_[B::grp()]; double* tile = WIDE ? tiles + B::grp() * PTILE_SW : tile_;
+    const int N = F.N, tid = B::tid(), t0 = blk * PTILE;
     const double* b = F.scratch;
-    double* z = F.scratch + N;
+    double* z = F.scratch + B::stride(N);
     if (tid <= PK) {
         const double rho = 1.0 / (7.0 + sqrt(48.0)), Cg = 6.0 / sqrt(48.0);   // rho = 7 - sqrt(48) without cancellation
         double g = Cg;
@@ -179,84 +216,97 @@ __device__ __forceinline__ void d_poisson_conv(VrtFields F, const double* part_b
         green[tid] = g;
     }
     double sb;
-    partial_prefix(part_b, G, 0, sh, &sb);
+    partial_prefix<WIDE>(part_b, G, 0, sh, &sb);
     for (int e = tid; e < PTILE + 2 * PK; e += PTHR) {
         int i = t0 - PK + e;                       // periodic wrap (N may be smaller than the halo)
         while (i < 0) i += N;
         while (i >= N) i -= N;
-        const double v = b[i];
-        tile[e] = (i == 0) ? v - sb : v;
+        const double v = b[B::at(i)];
+        tile[psw(e)] = (i == 0) ? v - sb : v;
     }
-    __syncthreads();
+    B::sync();
     double s = 0.0;
+    // tile entry tid * PEL + c sits at 5 tid + psw(c) (the padded layout above: no bank conflicts between the threads of a warp)
+    const double* mine = tile + 5 * tid;
+    const int zp0 = B::at(t0 + tid * PEL);
 #pragma unroll
     for (int k = 0; k < PEL; k++) {
-        const int e = tid * PEL + k + PK, i = t0 + tid * PEL + k;
+        const int i = t0 + tid * PEL + k;
         if (i < N) {
-            double acc = green[0] * tile[e];
-            for (int d = 1; d <= PK; d++) acc += green[d] * (tile[e + d] + tile[e - d]);
-            z[i] = acc; s += acc;
+            double acc = green[0] * mine[psw(k + PK)];
+#pragma unroll
+            for (int d = 1; d <= PK; d++) acc += green[d] * (mine[psw(k + PK + d)] + mine[psw(k + PK - d)]);
+            z[zp0 + k] = acc; s += acc;
         }
     }
-    const double t = block_sum(s, sh);
+    const double t = block_sum<WIDE>(s, sh);
     if (tid == 0) part_z[blk] = t;
-    if (blk == 0 && tid == 0) F.scratch[3L * N] = sb;
+    if (blk == 0 && tid == 0) F.scratch[3L * B::stride(N)] = sb;
 }
 
+template <bool WIDE>
 __device__ __forceinline__ void d_poisson_scan1(VrtFields F, const double* part_z, double* part_c, int G, const int blk) {
-    __shared__ double sh[40];
-    const int N = F.N, tid = threadIdx.x, i0 = blk * PTILE + tid * PEL;
-    const double* z = F.scratch + N;
-    double* cpre = F.scratch + 2L * N;
+    using B = Blk<WIDE>;
+    __shared__ double sh_[B::groups][40];
+    double* sh = sh_[B::grp()];
+    const int N = F.N, tid = B::tid(), i0 = blk * PTILE + tid * PEL, p0 = B::at(i0);
+    const double* z = F.scratch + B::stride(N);
+    double* cpre = F.scratch + 2L * B::stride(N);
     double tot;
-    const double base = partial_prefix(part_z, G, blk, sh, &tot);
+    const double base = partial_prefix<WIDE>(part_z, G, blk, sh, &tot);
     double v[PEL], loc = 0.0;
 #pragma unroll
-    for (int k = 0; k < PEL; k++) { v[k] = (i0 + k < N) ? z[i0 + k] : 0.0; loc += v[k]; }
-    double run = base + block_excl_scan(loc, sh, &tot), csum = 0.0;
+    for (int k = 0; k < PEL; k++) { v[k] = (i0 + k < N) ? z[p0 + k] : 0.0; loc += v[k]; }
+    double run = base + block_excl_scan<WIDE>(loc, sh, &tot), csum = 0.0;
 #pragma unroll
-    for (int k = 0; k < PEL; k++) if (i0 + k < N) { run += v[k]; cpre[i0 + k] = run; csum += run; }
-    const double t = block_sum(csum, sh);
+    for (int k = 0; k < PEL; k++) if (i0 + k < N) { run += v[k]; cpre[p0 + k] = run; csum += run; }
+    const double t = block_sum<WIDE>(csum, sh);
     if (tid == 0) part_c[blk] = t;
 }
 
+template <bool WIDE>
 __device__ __forceinline__ void d_poisson_dsum(VrtFields F, const double* part_c, double* part_d, int G, const int blk) {
-    __shared__ double sh[40];
-    const int N = F.N, tid = threadIdx.x, i0 = blk * PTILE + tid * PEL;
-    const double* cpre = F.scratch + 2L * N;
+    using B = Blk<WIDE>;
+    __shared__ double sh_[B::groups][40];
+    double* sh = sh_[B::grp()];
+    const int N = F.N, tid = B::tid(), i0 = blk * PTILE + tid * PEL, p0 = B::at(i0);
+    const double* cpre = F.scratch + 2L * B::stride(N);
     double csum;
-    partial_prefix(part_c, G, 0, sh, &csum);
+    partial_prefix<WIDE>(part_c, G, 0, sh, &csum);
     const double cmean = csum / (double)N;
     double loc = 0.0;
 #pragma unroll
-    for (int k = 0; k < PEL; k++) if (i0 + k < N) loc += (cmean - cpre[i0 + k]);
-    const double t = block_sum(loc, sh);
+    for (int k = 0; k < PEL; k++) if (i0 + k < N) loc += (cmean - cpre[p0 + k]);
+    const double t = block_sum<WIDE>(loc, sh);
     if (tid == 0) part_d[blk] = t;
 }
 
+template <bool WIDE>
 __device__ __forceinline__ void d_poisson_scan2(VrtFields F, const double* part_c, const double* part_d, int G, const int blk) {
-    __shared__ double sh[40];
-    const int N = F.N, tid = threadIdx.x, i0 = blk * PTILE + tid * PEL;
-    const double* cpre = F.scratch + 2L * N;
+    using B = Blk<WIDE>;
+    __shared__ double sh_[B::groups][40];
+    double* sh = sh_[B::grp()];
+    const int N = F.N, tid = B::tid(), i0 = blk * PTILE + tid * PEL, p0 = B::at(i0);
+    const double* cpre = F.scratch + 2L * B::stride(N);
     double csum, tot;
-    partial_prefix(part_c, G, 0, sh, &csum);
+    partial_prefix<WIDE>(part_c, G, 0, sh, &csum);
     const double cmean = csum / (double)N;
-    const double base = partial_prefix(part_d, G, blk, sh, &tot);
+    const double base = partial_prefix<WIDE>(part_d, G, blk, sh, &tot);
     double d[PEL], loc = 0.0;
 #pragma unroll
-    for (int k = 0; k < PEL; k++) { d[k] = (i0 + k < N) ? (cmean - cpre[i0 + k]) : 0.0; loc += d[k]; }
-    double run = base + block_excl_scan(loc, sh, &tot);
-    const double sb = F.scratch[3L * N];
+    for (int k = 0; k < PEL; k++) { d[k] = (i0 + k < N) ? (cmean - cpre[p0 + k]) : 0.0; loc += d[k]; }
+    double run = base + block_excl_scan<WIDE>(loc, sh, &tot);
+    const double sb = F.scratch[3L * B::stride(N)];
 #pragma unroll
     for (int k = 0; k < PEL; k++) if (i0 + k < N) { F.PHI[i0 + k] = (i0 + k == 0) ? sb : run; run += d[k]; }
 }
 
 
-__global__ void __launch_bounds__(PTHR) k_poisson_rhs(VrtFields F, double* part) { vrt_pdl_sync(); d_poisson_rhs(F, part, blockIdx.x); }
-__global__ void __launch_bounds__(PTHR) k_poisson_conv(VrtFields F, const double* part_b, double* part_z, int G) { vrt_pdl_sync(); d_poisson_conv(F, part_b, part_z, G, blockIdx.x); }
-__global__ void __launch_bounds__(PTHR) k_poisson_scan1(VrtFields F, const double* part_z, double* part_c, int G) { vrt_pdl_sync(); d_poisson_scan1(F, part_z, part_c, G, blockIdx.x); }
-__global__ void __launch_bounds__(PTHR) k_poisson_dsum(VrtFields F, const double* part_c, double* part_d, int G) { vrt_pdl_sync(); d_poisson_dsum(F, part_c, part_d, G, blockIdx.x); }
-__global__ void __launch_bounds__(PTHR) k_poisson_scan2(VrtFields F, const double* part_c, const double* part_d, int G) { vrt_pdl_sync(); d_poisson_scan2(F, part_c, part_d, G, blockIdx.x); }
+__global__ void __launch_bounds__(PTHR) k_poisson_rhs(VrtFields F, double* part) { vrt_pdl_sync(); d_poisson_rhs<false>(F, part, blockIdx.x); }
+__global__ void __launch_bounds__(PTHR) k_poisson_conv(VrtFields F, const double* part_b, double* part_z, int G) { vrt_pdl_sync(); d_poisson_conv<false>(F, part_b, part_z, G, blockIdx.x); }
+__global__ void __launch_bounds__(PTHR) k_poisson_scan1(VrtFields F, const double* part_z, double* part_c, int G) { vrt_pdl_sync(); d_poisson_scan1<false>(F, part_z, part_c, G, blockIdx.x); }
+__global__ void __launch_bounds__(PTHR) k_poisson_dsum(VrtFields F, const double* part_c, double* part_d, int G) { vrt_pdl_sync(); d_poisson_dsum<false>(F, part_c, part_d, G, blockIdx.x); }
+__global__ void __launch_bounds__(PTHR) k_poisson_scan2(VrtFields F, const double* part_c, const double* part_d, int G) { vrt_pdl_sync(); d_poisson_scan2<false>(F, part_c, part_d, G, blockIdx.x); }
 
 // EMFieldSolver::GetEfield without the Ex0 term (EMSolver.cpp:137-154)
 __device__ __forceinline__ double efield_base(const VrtFields& F, int i) {
@@ -290,18 +340,17 @@ __global__ void k_commit_ex0(VrtFields F) { vrt_pdl_sync(); F.Ex0[0] = F.Ex0[1];
 // same bits — then tabulates E and commits Ex0.
 // The three N-vectors the passes hand to each other (b, z, prefix of z) and sum(b) live in shared memory here (3N + 1 doubles,
 // <= 96 KB) instead of the global scratch: a single CTA would otherwise pay a global-memory round trip between every pair of passes.
-constexpr int PSMALL = 4;
 __global__ void __launch_bounds__(PTHR) k_poisson_small(VrtFields F, double* part, int G) {
     vrt_pdl_sync();
     extern __shared__ __align__(16) double psm[];
     F.scratch = psm;
     part = psm + 3L * F.N + 8;            // the tile partials of the four passes too (PSMALL entries each)
-    for (int blk = 0; blk < G; blk++) d_poisson_rhs(F, part, blk);
+    for (int blk = 0; blk < G; blk++) d_poisson_rhs<false>(F, part, blk);
     __syncthreads();
-    for (int blk = 0; blk < G; blk++) { d_poisson_conv(F, part, part + 8, G, blk); __syncthreads(); }
-    for (int blk = 0; blk < G; blk++) { d_poisson_scan1(F, part + 8, part + 16, G, blk); __syncthreads(); }
-    for (int blk = 0; blk < G; blk++) { d_poisson_dsum(F, part + 16, part + 24, G, blk); __syncthreads(); }
-    for (int blk = 0; blk < G; blk++) { d_poisson_scan2(F, part + 16, part + 24, G, blk); __syncthreads(); }
+    for (int blk = 0; blk < G; blk++) { d_poisson_conv<false>(F, part, part + 8, G, blk); __syncthreads(); }
+    for (int blk = 0; blk < G; blk++) { d_poisson_scan1<false>(F, part + 8, part + 16, G, blk); __syncthreads(); }
+    for (int blk = 0; blk < G; blk++) { d_poisson_dsum<false>(F, part + 16, part + 24, G, blk); __syncthreads(); }
+    for (int blk = 0; blk < G; blk++) { d_poisson_scan2<false>(F, part + 16, part + 24, G, blk); __syncthreads(); }
     __shared__ double ex0_new;
     if (threadIdx.x == 0) {
         const double ex0 = *F.Ex0;
@@ -309,6 +358,36 @@ __global__ void __launch_bounds__(PTHR) k_poisson_small(VrtFields F, double* par
     }
     __syncthreads();
     for (int i = (int)threadIdx.x - F.epad; i < F.N + F.epad; i += PTHR) F.E[i + F.epad] = efield_base(F, i) + ex0_new;
+    if (threadIdx.x == 0) { F.Ex0[1] = ex0_new; F.Ex0[0] = ex0_new; }
+}
+
+// The tiles side by side inside ONE CTA: G groups of PTHR threads, one tile each (Blk<true>: named barriers inside a group, a
+// CTA-wide barrier where the multi-CTA version has kernel boundaries), the three N-vectors and the tile partials in shared memory.
+// Neither the global-memory round trips between the passes (cluster kernel) nor the walk over the tiles (single-block kernel).
+__global__ void __launch_bounds__(PSMALL * PTHR) k_poisson_wide(VrtFields F, int G) {
+    vrt_pdl_sync();
+    extern __shared__ __align__(16) double psm[];
+    F.scratch = psm;                                        // three padded N-vectors, sum(b), the tile partials, the groups' staged tiles
+    double* part = psm + 3L * psw_len(F.N) + 8;
+    double* tiles = part + 32;
+    const int blk = Blk<true>::grp();                       // blockDim.x = G * PTHR: every group has a tile
+    d_poisson_rhs<true>(F, part, blk);
+    __syncthreads();
+    d_poisson_conv<true>(F, part, part + 8, G, blk, tiles);
+    __syncthreads();
+    d_poisson_scan1<true>(F, part + 8, part + 16, G, blk);
+    __syncthreads();
+    d_poisson_dsum<true>(F, part + 16, part + 24, G, blk);
+    __syncthreads();
+    d_poisson_scan2<true>(F, part + 16, part + 24, G, blk);
+    __syncthreads();
+    __shared__ double ex0_new;
+    if (threadIdx.x == 0) {
+        const double ex0 = *F.Ex0;
+        ex0_new = ex0 + -((efield_base(F, -1) + ex0) + (efield_base(F, 0) + ex0)) * 0.5;
+    }
+    __syncthreads();
+    for (int i = (int)threadIdx.x - F.epad; i < F.N + F.epad; i += (int)blockDim.x) F.E[i + F.epad] = efield_base(F, i) + ex0_new;
     if (threadIdx.x == 0) { F.Ex0[1] = ex0_new; F.Ex0[0] = ex0_new; }
 }
 
@@ -324,15 +403,15 @@ __global__ void __launch_bounds__(PTHR) k_poisson_cluster(VrtFields F, double* p
     vrt_pdl_sync();
     const int blk = blockIdx.x, nc = gridDim.x;            // nc = cluster size (>= G, a power of two); CTAs beyond G only keep the barriers
     const bool work = blk < G;
-    if (work) d_poisson_rhs(F, part, blk);
+    if (work) d_poisson_rhs<false>(F, part, blk);
     cluster_sync_all();
-    if (work) d_poisson_conv(F, part, part + PMAXT, G, blk);
+    if (work) d_poisson_conv<false>(F, part, part + PMAXT, G, blk);
     cluster_sync_all();
-    if (work) d_poisson_scan1(F, part + PMAXT, part + 2 * PMAXT, G, blk);
+    if (work) d_poisson_scan1<false>(F, part + PMAXT, part + 2 * PMAXT, G, blk);
     cluster_sync_all();
-    if (work) d_poisson_dsum(F, part + 2 * PMAXT, part + 3 * PMAXT, G, blk);
+    if (work) d_poisson_dsum<false>(F, part + 2 * PMAXT, part + 3 * PMAXT, G, blk);
     cluster_sync_all();
-    if (work) d_poisson_scan2(F, part + 2 * PMAXT, part + 3 * PMAXT, G, blk);
+    if (work) d_poisson_scan2<false>(F, part + 2 * PMAXT, part + 3 * PMAXT, G, blk);
     cluster_sync_all();
     __shared__ double ex0_new;
     if (threadIdx.x == 0) {
@@ -445,8 +524,19 @@ int vrt_fields_poisson(vrt_ctx* c) {
     const int G = (F.N + PTILE - 1) / PTILE;
     if (G > PMAXT) { c->err = "vrt_poisson: x_size_finest too large for the tiled solver"; return VRT_ERR_ARG; }
     double* part = F.scratch + 3L * F.N + 8;      // 4 arrays of PMAXT tile partials behind the three N-vectors and sum(b)
-    // short grids: VRT_POISSON_SMALL = 2 (default) one cluster launch, 1 one single-CTA launch, 0 the multi-kernel passes (tests)
-    const int small_mode = getenv("VRT_POISSON_SMALL") ? atoi(getenv("VRT_POISSON_SMALL")) : 2;
+    // short grids: VRT_POISSON_SMALL = 3 (default) one wide CTA with a thread group per tile, 2 one cluster launch, 1 one block walking the
+    // tiles, 0 the multi-kernel passes (tests; profiles/ab_poisson_r2v.txt: 16 us against 25 us for the cluster at N = 2048)
+    const int small_mode = getenv("VRT_POISSON_SMALL") ? atoi(getenv("VRT_POISSON_SMALL")) : 3;
+    if (G <= PSMALL && small_mode == 3) {       // one CTA, the tiles side by side as thread groups
+        const size_t smem = sizeof(double) * (3 * (size_t)psw_len(F.N) + 8 + 32 + (size_t)G * PTILE_SW);
+        static bool attr_dev[64] = {};
+        bool& attr = attr_dev[c->device & 63];
+        if (!attr) { VRT_CUDA(c, cudaFuncSetAttribute(k_poisson_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (3 * psw_len(PSMALL * PTILE) + 8 + 32 + PSMALL * PTILE_SW)))); attr = true; }
+        vrt_launch_smem(k_poisson_wide, dim3(1), dim3(G * PTHR), smem, c->stream, F, G);
+        c->launches += 1;
+        VRT_CUDA(c, cudaGetLastError());
+        return 0;
+    }
     if (G <= PSMALL && small_mode == 2) {
         unsigned nc = 1;
         while ((int)nc < G) nc <<= 1;
