@@ -175,6 +175,24 @@ __device__ double partial_prefix(const double* part, int G, int blk, double* sh,
     const int cp = (G + PTHR - 1) / PTHR, lo = B::tid() * cp, hi = min(G, lo + cp);
     double loc = 0.0, before = 0.0;
     for (int k = lo; k < hi; k++) { if (k == blk) before = loc; loc += part[k]; }
+    if (WIDE) {
+        // G <= PSMALL: every partial sits in the first warp of the group (one per thread), the other warps hold zeros.  The general
+        // scan below then reduces to the first warp's shuffle scan plus additions of +0.0 — written out here with exactly those
+        // additions (x + 0.0 is not an identity for -0.0 and is not folded away), without the second phase and two of the barriers.
+        __shared__ double tot_[B::groups];
+        B::sync();
+        if (B::tid() < 32) {
+            const int lane = B::tid();
+            double inc = loc;
+            for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            const double all = __shfl_sync(0xffffffffu, inc, 31);
+            if (lane == blk) own[B::grp()] = (0.0 + (inc - loc)) + before;
+            if (lane == 0) tot_[B::grp()] = 0.0 + all;
+        }
+        B::sync();
+        *total = tot_[B::grp()];
+        return own[B::grp()];
+    }
     const double off = block_excl_scan<WIDE>(loc, sh, total);
     if (blk >= lo && blk < hi) own[B::grp()] = off + before;
     B::sync();
@@ -282,7 +300,7 @@ __device__ __forceinline__ void d_poisson_dsum(VrtFields F, const double* part_c
 }
 
 template <bool WIDE>
-__device__ __forceinline__ void d_poisson_scan2(VrtFields F, const double* part_c, const double* part_d, int G, const int blk) {
+__device__ __forceinline__ void d_poisson_scan2(VrtFields F, const double* part_c, const double* part_d, int G, const int blk, double* phi_s = nullptr) {
     using B = Blk<WIDE>;
     __shared__ double sh_[B::groups][40];
     double* sh = sh_[B::grp()];
@@ -298,7 +316,12 @@ __device__ __forceinline__ void d_poisson_scan2(VrtFields F, const double* part_
     double run = base + block_excl_scan<WIDE>(loc, sh, &tot);
     const double sb = F.scratch[3L * B::stride(N)];
 #pragma unroll
-    for (int k = 0; k < PEL; k++) if (i0 + k < N) { F.PHI[i0 + k] = (i0 + k == 0) ? sb : run; run += d[k]; }
+    for (int k = 0; k < PEL; k++) if (i0 + k < N) {
+        const double phi = (i0 + k == 0) ? sb : run;
+        F.PHI[i0 + k] = phi;
+        if (WIDE) phi_s[p0 + k] = phi;           // the wide kernel tabulates E from this copy (padded layout, over the dead b vector)
+        run += d[k];
+    }
 }
 
 
@@ -309,15 +332,18 @@ __global__ void __launch_bounds__(PTHR) k_poisson_dsum(VrtFields F, const double
 __global__ void __launch_bounds__(PTHR) k_poisson_scan2(VrtFields F, const double* part_c, const double* part_d, int G) { vrt_pdl_sync(); d_poisson_scan2<false>(F, part_c, part_d, G, blockIdx.x); }
 
 // EMFieldSolver::GetEfield without the Ex0 term (EMSolver.cpp:137-154)
-__device__ __forceinline__ double efield_base(const VrtFields& F, int i) {
-    const int N = F.N;
+template <class Phi>
+__device__ __forceinline__ double efield_of(const Phi& PHI, const int N, const double dx, int i) {
     int ip1 = i + 1, im1 = i - 1, ip2 = i + 2, im2 = i - 2;
     ip1 = ip1 > -1 ? ip1 : ip1 + N; im1 = im1 > -1 ? im1 : im1 + N;
     ip2 = ip2 > -1 ? ip2 : ip2 + N; im2 = im2 > -1 ? im2 : im2 + N;
     ip1 = ip1 < N ? ip1 : ip1 - N; im1 = im1 < N ? im1 : im1 - N;
     ip2 = ip2 < N ? ip2 : ip2 - N; im2 = im2 < N ? im2 : im2 - N;
-    const double fieldCoef = 1.0 / (12 * F.dx);
-    return -fieldCoef * (8 * (F.PHI[ip1] - F.PHI[im1]) - F.PHI[ip2] + F.PHI[im2]);
+    const double fieldCoef = 1.0 / (12 * dx);
+    return -fieldCoef * (8 * (PHI(ip1) - PHI(im1)) - PHI(ip2) + PHI(im2));
+}
+__device__ __forceinline__ double efield_base(const VrtFields& F, int i) {
+    return efield_of([&](int k) { return F.PHI[k]; }, F.N, F.dx, i);
 }
 // Ex0 += -(GetEfield(-1)+GetEfield(0))*0.5 (EMSolver.cpp:191, quirk Q4), then tabulate E on [-epad, N+epad)
 __global__ void k_efield(VrtFields F, int update_ex0) { vrt_pdl_sync();
@@ -370,6 +396,7 @@ __global__ void __launch_bounds__(PSMALL * PTHR) k_poisson_wide(VrtFields F, int
     F.scratch = psm;                                        // three padded N-vectors, sum(b), the tile partials, the groups' staged tiles
     double* part = psm + 3L * psw_len(F.N) + 8;
     double* tiles = part + 32;
+    const double ex0 = *F.Ex0;                              // only this kernel writes Ex0: fetched now, used after the last pass
     const int blk = Blk<true>::grp();                       // blockDim.x = G * PTHR: every group has a tile
     d_poisson_rhs<true>(F, part, blk);
     __syncthreads();
@@ -379,15 +406,13 @@ __global__ void __launch_bounds__(PSMALL * PTHR) k_poisson_wide(VrtFields F, int
     __syncthreads();
     d_poisson_dsum<true>(F, part + 16, part + 24, G, blk);
     __syncthreads();
-    d_poisson_scan2<true>(F, part + 16, part + 24, G, blk);
+    d_poisson_scan2<true>(F, part + 16, part + 24, G, blk, psm);
     __syncthreads();
     __shared__ double ex0_new;
-    if (threadIdx.x == 0) {
-        const double ex0 = *F.Ex0;
-        ex0_new = ex0 + -((efield_base(F, -1) + ex0) + (efield_base(F, 0) + ex0)) * 0.5;
-    }
+    const auto phi = [&](int k) { return psm[Blk<true>::at(k)]; };
+    if (threadIdx.x == 0) ex0_new = ex0 + -((efield_of(phi, F.N, F.dx, -1) + ex0) + (efield_of(phi, F.N, F.dx, 0) + ex0)) * 0.5;
     __syncthreads();
-    for (int i = (int)threadIdx.x - F.epad; i < F.N + F.epad; i += (int)blockDim.x) F.E[i + F.epad] = efield_base(F, i) + ex0_new;
+    for (int i = (int)threadIdx.x - F.epad; i < F.N + F.epad; i += (int)blockDim.x) F.E[i + F.epad] = efield_of(phi, F.N, F.dx, i) + ex0_new;
     if (threadIdx.x == 0) { F.Ex0[1] = ex0_new; F.Ex0[0] = ex0_new; }
 }
 
